@@ -1,0 +1,248 @@
+/*
+ * bgp.h — C ABI of the B200-native GP covariance engine (libbgp_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of dfm/george:
+ *     gp.compute(x, yerr) + gp.log_likelihood(y) (+ gp.predict on the same factorisation)
+ * i.e. kernel-matrix build -> factorisation (dense Cholesky | HODLR) -> log-det -> solve -> quadratic form.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, returns an int status
+ * (0 = BGP_OK) and never lets a C++ exception cross the boundary; the message for the last
+ * failing call on the calling thread is available from bgp_last_error().
+ *
+ * Each function names the reference interface it replaces (paths relative to the dfm/george
+ * checkout, commit b5023758).  Host pointers are borrowed for the duration of a call only
+ * (the reference copies its inputs as well: src/george/solvers/_hodlr.cpp:71-81,156-164).
+ * Pointers are HOST pointers unless the name ends in `_dev`.
+ */
+#ifndef BGP_B200_H_
+#define BGP_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Status codes.  The Python host maps them to the exception types the reference raises
+ * (SURVEY.md §8b "Errors"): DIM -> RuntimeError (george::dimension_mismatch, exceptions.h:8-12),
+ * NOT_COMPUTED -> RuntimeError (exceptions.h:14-18), INVALID -> ValueError (std::invalid_argument,
+ * parser.h:16,33,505), INDEX -> IndexError (_hodlr.cpp:26), LINALG -> numpy.linalg.LinAlgError
+ * (what scipy.linalg.cholesky raises, solvers/basic.py:68).
+ * ------------------------------------------------------------------------------------------ */
+enum {
+  BGP_OK = 0,
+  BGP_ERR_INVALID = 1,       /* malformed kernel program / argument                              */
+  BGP_ERR_DIM = 2,           /* dimension mismatch between x and the kernel                      */
+  BGP_ERR_NOT_COMPUTED = 3,  /* solve before compute                                             */
+  BGP_ERR_LINALG = 4,        /* matrix not positive definite (dense path only)                   */
+  BGP_ERR_CUDA = 5,          /* CUDA runtime failure; no CPU fallback exists                     */
+  BGP_ERR_NO_DEVICE = 6,     /* no sm_100 device visible: the library refuses to run             */
+  BGP_ERR_RANK_CAPACITY = 7, /* ACA rank exceeded the configured capacity (see bgp_hodlr_opts_t) */
+  BGP_ERR_INDEX = 8,
+  BGP_ERR_NOMEM = 9
+};
+
+const char* bgp_last_error(void);
+/* Library/ABI version (major*1000+minor). */
+int bgp_version(void);
+/* Number of visible CUDA devices with compute capability 10.x; 0 if none (never an error). */
+int bgp_device_count(void);
+/* Select the CUDA device used by subsequently created handles of the calling thread. */
+int bgp_set_device(int device);
+/* Count of kernel launches issued by this library since process start (bench.py "gpu_launches"). */
+uint64_t bgp_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Kernel program: the POD form of the Python kernel-spec tree that the reference walks with
+ * pybind11 attribute reads (src/george/include/george/parser.h:14-509).  Nodes are in POSTFIX
+ * order (operands before their operator), so the flattened hyper-parameter vector is the
+ * concatenation over leaves in program order — the order Operator::set_parameter uses
+ * (kernels.h:56-69) — with, inside a stationary leaf, the kernel's own parameters first and the
+ * metric parameters after them (kernels.h:1870-1875, size() at kernels.h:2005).
+ * ------------------------------------------------------------------------------------------ */
+#define BGP_MAX_DIM 8      /* max axes a kernel leaf may act on                                  */
+#define BGP_MAX_METRIC 36  /* BGP_MAX_DIM*(BGP_MAX_DIM+1)/2 packed-Cholesky entries (metrics.h:166-168) */
+#define BGP_MAX_NODES 32   /* max nodes (leaves + operators) of one program                       */
+
+enum { BGP_OP_KERNEL = 0, BGP_OP_SUM = 1, BGP_OP_PRODUCT = 2 }; /* kernels.py:234-247 operator_type+1 */
+
+/* kernel_type ids are the reference's (kernels.py: kernel_type attributes; parser.h:40-505). */
+enum {
+  BGP_K_LINEAR = 0, BGP_K_RATIONAL_QUADRATIC = 1, BGP_K_EXP = 2, BGP_K_LOCAL_GAUSSIAN = 3,
+  BGP_K_EMPTY = 4, BGP_K_COSINE = 5, BGP_K_MATERN52 = 6, BGP_K_EXP_SINE2 = 7, BGP_K_CONSTANT = 8,
+  BGP_K_EXP_SQUARED = 9, BGP_K_MATERN32 = 10, BGP_K_POLYNOMIAL = 11, BGP_K_DOT_PRODUCT = 12
+};
+enum { BGP_METRIC_NONE = -1, BGP_METRIC_ISOTROPIC = 0, BGP_METRIC_AXIS_ALIGNED = 1, BGP_METRIC_GENERAL = 2 };
+
+typedef struct bgp_kernel_node {
+  int32_t op;           /* BGP_OP_*                                                              */
+  int32_t kernel_type;  /* BGP_K_* (leaf only)                                                   */
+  int32_t metric_type;  /* BGP_METRIC_* ; NONE for the non-stationary kernels                    */
+  int32_t ndim;         /* dimension of the input space                                          */
+  int32_t naxes;        /* number of axes the leaf acts on (subspace.h:10-25)                    */
+  int32_t blocked;      /* stationary kernels: block mask active (kernels.h:1897-1905)           */
+  int32_t n_params;     /* number of the kernel's own hyper-parameters (excl. metric)            */
+  int32_t n_metric;     /* number of metric parameters (1 | naxes | naxes(naxes+1)/2)            */
+  int32_t axes[BGP_MAX_DIM];
+  /* raw Python-side values, exactly what parser.h passes to the constructors:
+   *   Linear: {log_gamma2, order}   RationalQuadratic: {log_alpha}   LocalGaussian: {location, log_width}
+   *   Cosine: {log_period}   ExpSine2: {gamma, log_period}   Constant: {log_constant}
+   *   Polynomial: {log_sigma2, order}   (order is a constant, not a hyper-parameter)                  */
+  double params[4];
+  double metric[BGP_MAX_METRIC];    /* metric.get_parameter_vector(include_frozen=True) (parser.h:111-116) */
+  double min_block[BGP_MAX_DIM];
+  double max_block[BGP_MAX_DIM];
+} bgp_kernel_node_t;
+
+typedef struct bgp_kernel_spec {
+  int32_t n_nodes;
+  int32_t ndim;
+  bgp_kernel_node_t nodes[BGP_MAX_NODES];
+} bgp_kernel_spec_t;
+
+/* Validate a program (stack discipline, ids, dimensions).  Replaces the checks in parser.h:16-37,505. */
+int bgp_spec_validate(const bgp_kernel_spec_t* spec);
+/* Total number of hyper-parameters = Kernel::size() (kernels.h:56, 2005). */
+int bgp_spec_num_params(const bgp_kernel_spec_t* spec, int* n_params);
+
+/* ------------------------------------------------------------------------------------------
+ * Kernel-matrix build.  Replaces KernelInterface::value_symmetric / value_general / value_diagonal
+ * (src/george/kernel_interface.cpp:62-77, 47-60, 79-90) and gradient_symmetric / gradient_general
+ * (kernel_interface.cpp:109-125, 92-107).  x1: (n1, ndim) row-major f64; out row-major f64.
+ * `which` (n_params uint32) selects the hyper-parameters to differentiate; unselected slices are 0.
+ * The *_dev variants take device pointers and run on the handle-less default stream of the
+ * calling thread's device; they are what the solvers call internally.
+ * ------------------------------------------------------------------------------------------ */
+int bgp_kmat_symmetric(const bgp_kernel_spec_t* spec, const double* x, int64_t n, double* out /* n*n */);
+int bgp_kmat_general(const bgp_kernel_spec_t* spec, const double* x1, int64_t n1, const double* x2, int64_t n2,
+                     double* out /* n1*n2 */);
+int bgp_kmat_diagonal(const bgp_kernel_spec_t* spec, const double* x1, const double* x2, int64_t n,
+                      double* out /* n */);
+int bgp_kmat_gradient_symmetric(const bgp_kernel_spec_t* spec, const uint32_t* which, const double* x, int64_t n,
+                                double* out /* n*n*n_params */);
+int bgp_kmat_gradient_general(const bgp_kernel_spec_t* spec, const uint32_t* which, const double* x1, int64_t n1,
+                              const double* x2, int64_t n2, double* out /* n1*n2*n_params */);
+/* device-resident build: out_dev[i*ld + j] (row-major, ld >= n2); diag_add_dev (may be NULL, symmetric only)
+ * is added on the diagonal — the fusion of solvers/basic.py:64-65. */
+int bgp_kmat_symmetric_dev(const bgp_kernel_spec_t* spec, const double* x_dev, int64_t n, const double* diag_add_dev,
+                           double* out_dev, int64_t ld);
+int bgp_kmat_general_dev(const bgp_kernel_spec_t* spec, const double* x1_dev, int64_t n1, const double* x2_dev,
+                         int64_t n2, double* out_dev, int64_t ld);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense solver.  Replaces BasicSolver (src/george/solvers/basic.py:51-121): kernel matrix +
+ * yerr^2 on the diagonal, Cholesky, log-det = 2 sum log diag, cho_solve, r @ U, dense inverse.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct bgp_dense bgp_dense_t;
+int bgp_dense_create(bgp_dense_t** out);
+void bgp_dense_destroy(bgp_dense_t* h);
+/* basic.py:51-70.  yerr is the standard deviation; yerr^2 is added on the diagonal. */
+int bgp_dense_compute(bgp_dense_t* h, const bgp_kernel_spec_t* spec, const double* x, int64_t n, int32_t ndim,
+                      const double* yerr);
+int bgp_dense_computed(const bgp_dense_t* h);
+int bgp_dense_log_determinant(const bgp_dense_t* h, double* out);
+/* basic.py:72-87.  b: (n, nrhs) column-major with leading dimension ldb (a plain vector has nrhs=1); in place. */
+int bgp_dense_apply_inverse(bgp_dense_t* h, double* b, int64_t nrhs, int64_t ldb);
+/* basic.py:89-102 */
+int bgp_dense_dot_solve(bgp_dense_t* h, const double* y, double* out);
+/* basic.py:104-114: out = r @ U with r (nr, n) row-major, out (nr, n) row-major, U the upper factor. */
+int bgp_dense_apply_sqrt(bgp_dense_t* h, const double* r, int64_t nr, double* out);
+/* basic.py:116-121: out (n, n); symmetric so the order does not matter. */
+int bgp_dense_get_inverse(bgp_dense_t* h, double* out);
+/* timing of the last compute: [0]=kernel-matrix build ms, [1]=potrf ms (device events). */
+int bgp_dense_last_timing(const bgp_dense_t* h, double* ms2);
+
+/* ------------------------------------------------------------------------------------------
+ * HODLR solver.  Replaces _hodlr.HODLRSolver (src/george/solvers/_hodlr.cpp:115-204) and the
+ * hodlr::Node tree behind it (src/george/include/george/hodlr.h:13-256).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct bgp_hodlr bgp_hodlr_t;
+
+enum {
+  BGP_RNG_PER_NODE = 0, /* each tree node draws from its own mt19937 stream (level-parallel build)     */
+  BGP_RNG_REFERENCE = 1 /* one mt19937 threaded through the pre-order recursion, as hodlr.h:35,58-61   */
+};
+
+typedef struct bgp_hodlr_opts {
+  int32_t min_size;      /* default 100 (_hodlr.cpp:202)                                         */
+  int32_t seed;          /* default 42                                                            */
+  double  tol;           /* default 0.1                                                           */
+  int32_t rng_mode;      /* BGP_RNG_*                                                             */
+  int32_t rank_capacity; /* max columns kept per low-rank factor; 0 = automatic                   */
+  /* multi-GPU sharding by top-level sub-tree: this process owns sub-tree
+   * `shard_rank` of `shard_count` (a power of two; 1 = whole tree).                             */
+  int32_t shard_rank;
+  int32_t shard_count;
+  int32_t reserved;
+} bgp_hodlr_opts_t;
+
+void bgp_hodlr_default_opts(bgp_hodlr_opts_t* o);
+int bgp_hodlr_create(bgp_hodlr_t** out);
+void bgp_hodlr_destroy(bgp_hodlr_t* h);
+/* _hodlr.cpp:55-94 (Solver::compute): snapshot kernel + x, diag = yerr^2, build and factor the tree. */
+int bgp_hodlr_compute(bgp_hodlr_t* h, const bgp_kernel_spec_t* spec, const double* x, int64_t n, int32_t ndim,
+                      const double* yerr, const bgp_hodlr_opts_t* opts);
+/* same with x / yerr already resident on the device (bench "value" leg; inputs in HBM). */
+int bgp_hodlr_compute_dev(bgp_hodlr_t* h, const bgp_kernel_spec_t* spec, const double* x_dev, int64_t n,
+                          int32_t ndim, const double* yerr_dev, const bgp_hodlr_opts_t* opts);
+int bgp_hodlr_computed(const bgp_hodlr_t* h);               /* _hodlr.cpp:123 */
+int bgp_hodlr_log_determinant(const bgp_hodlr_t* h, double* out); /* _hodlr.cpp:124 */
+/* _hodlr.cpp:156-164: b (n, nrhs) column-major, leading dimension ldb, solved in place. */
+int bgp_hodlr_apply_inverse(bgp_hodlr_t* h, double* b, int64_t nrhs, int64_t ldb);
+/* _hodlr.cpp:178-182 */
+int bgp_hodlr_dot_solve(bgp_hodlr_t* h, const double* y, double* out);
+int bgp_hodlr_dot_solve_dev(bgp_hodlr_t* h, const double* y_dev, double* out);
+/* _hodlr.cpp:193-199: dense inverse (n, n). */
+int bgp_hodlr_get_inverse(bgp_hodlr_t* h, double* out);
+
+/* Tree / index structure introspection (bit-exact parity target; hodlr.h:48-61).
+ * Nodes are listed in the reference's PRE-ORDER construction order. */
+typedef struct bgp_hodlr_node_info {
+  int32_t start, size, half; /* half = size/2 (hodlr.h:48); children are [start,half) and [start+half,size-half) */
+  int32_t is_leaf;
+  int32_t parent;            /* pre-order index of the parent, -1 for the root                     */
+  int32_t direction;         /* 0 = left child, 1 = right child (hodlr.h:58-61)                    */
+  int32_t depth;
+  int32_t rank;              /* ACA rank of the node's off-diagonal block (0 for leaves)           */
+  int32_t rng_draws;         /* number of mt19937 words the node's ACA consumed                    */
+  int32_t dense_fallback;    /* 1 if the rows ran out and the dense factorisation was returned (hodlr.h:161-176) */
+} bgp_hodlr_node_info_t;
+int bgp_hodlr_num_nodes(const bgp_hodlr_t* h, int64_t* out);
+int bgp_hodlr_node_info(const bgp_hodlr_t* h, bgp_hodlr_node_info_t* out /* num_nodes */);
+/* ACA pivots of node `node` (pre-order index): rows[k], cols[k] for k < rank, block-relative. */
+int bgp_hodlr_node_pivots(const bgp_hodlr_t* h, int64_t node, int32_t* rows, int32_t* cols);
+/* Device-event timings of the last compute, ms: [0] leaves (build+factor), [1] ACA, [2] up-sweep,
+ * [3] total compute, [4] last solve. */
+int bgp_hodlr_last_timing(const bgp_hodlr_t* h, double* ms5);
+/* Algorithmic work of the last compute: [0] kernel evaluations, [1] bytes, [2] flops,
+ * [3] sum of per-level max ranks R, [4] leaf size m, [5] number of levels. */
+int bgp_hodlr_last_work(const bgp_hodlr_t* h, double* w6);
+
+/* Multi-GPU exchange step: after the local sub-tree is factored, the rows this
+ * shard owns of the shared top-level factor panel are exported, all-gathered by the host
+ * (torch.distributed / NCCL), imported, and the top nodes are finished redundantly.
+ *   bgp_hodlr_top_panel(h, &ptr_dev, &rows, &cols, &ld): device pointer to the (N x cols) column-major panel
+ *   bgp_hodlr_finish_top(h): Gram/LU/log-det/update of the nodes above the shard cut.               */
+int bgp_hodlr_top_panel(bgp_hodlr_t* h, double** ptr_dev, int64_t* row0, int64_t* rows, int64_t* cols, int64_t* ld);
+int bgp_hodlr_finish_top(bgp_hodlr_t* h);
+/* sharded solve: local part, then (host all-gathers the vector), then top part. */
+int bgp_hodlr_solve_local_dev(bgp_hodlr_t* h, double* b_dev, int64_t nrhs, int64_t ldb);
+int bgp_hodlr_solve_top_dev(bgp_hodlr_t* h, double* b_dev, int64_t nrhs, int64_t ldb);
+
+/* ------------------------------------------------------------------------------------------
+ * Device memory helpers so a host without torch can stage inputs (bench "value" leg).
+ * ------------------------------------------------------------------------------------------ */
+int bgp_dev_alloc(void** ptr_dev, size_t bytes);
+int bgp_dev_free(void* ptr_dev);
+int bgp_dev_upload(void* dst_dev, const void* src_host, size_t bytes);
+int bgp_dev_download(void* dst_host, const void* src_dev, size_t bytes);
+int bgp_dev_synchronize(void);
+int bgp_host_alloc_pinned(void** ptr, size_t bytes);
+int bgp_host_free_pinned(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGP_B200_H_ */
