@@ -65,6 +65,8 @@ SIGNATURES = {
     "bgp_dense_dot_solve": (C.c_int, [_p, _p, _dp]),
     "bgp_dense_apply_sqrt": (C.c_int, [_p, _p, _i64, _p]),
     "bgp_dense_get_inverse": (C.c_int, [_p, _p]),
+    "bgp_dense_export_factor": (C.c_int, [_p, _p]),
+    "bgp_dense_import_factor": (C.c_int, [_p, _p, _i64, C.c_double]),
     "bgp_dense_last_timing": (C.c_int, [_p, _dp]),
     "bgp_hodlr_default_opts": (None, [C.POINTER(HodlrOpts)]),
     "bgp_hodlr_create": (C.c_int, [C.POINTER(_p)]),
@@ -84,6 +86,9 @@ SIGNATURES = {
     "bgp_hodlr_last_work": (C.c_int, [_p, _dp]),
     "bgp_hodlr_top_panel": (C.c_int, [_p, C.POINTER(_p), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
                                       C.POINTER(_i64)]),
+    "bgp_hodlr_export_top": (C.c_int, [_p, _p, _i64]),
+    "bgp_hodlr_import_top": (C.c_int, [_p, _p, _i64]),
+    "bgp_hodlr_shard_rows": (C.c_int, [_p, _i32, C.POINTER(_i64), C.POINTER(_i64)]),
     "bgp_hodlr_finish_top": (C.c_int, [_p]),
     "bgp_hodlr_solve_local_dev": (C.c_int, [_p, _p, _i64, _i64]),
     "bgp_hodlr_solve_top_dev": (C.c_int, [_p, _p, _i64, _i64]),

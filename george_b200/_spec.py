@@ -40,7 +40,7 @@ class KernelSpec(C.Structure):
 class HodlrOpts(C.Structure):
     _fields_ = [
         ("min_size", C.c_int32), ("seed", C.c_int32), ("tol", C.c_double), ("rng_mode", C.c_int32),
-        ("rank_capacity", C.c_int32), ("shard_rank", C.c_int32), ("shard_count", C.c_int32), ("reserved", C.c_int32),
+        ("rank_capacity", C.c_int32), ("shard_rank", C.c_int32), ("shard_count", C.c_int32), ("exhaust_mode", C.c_int32),
     ]
 
 

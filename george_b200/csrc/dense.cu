@@ -1,0 +1,463 @@
+// dense.cu — K3: dense solver behind BasicSolver (replaces src/george/solvers/basic.py:51-121, i.e.
+// kernel.get_value + scipy.linalg.cholesky / cho_solve, LAPACK dpotrf/dpotrs).
+//
+// The covariance matrix is generated on the device by the fused kernel-matrix build (kmat.cu) with yerr^2 already on
+// the diagonal, factorised in place (blocked right-looking Cholesky, lower factor L with K = L L^T; the reference keeps
+// the upper factor U = L^T, basic.py:68) and never leaves HBM.  log-det = 2 sum log L_ii (basic.py:69).
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "kernel_eval.cuh"
+
+namespace bgp {
+int upload_program(const DevProgram& P, DevBuf<DevProgram>& buf, cudaStream_t s);
+int kmat_symmetric_launch(const DevProgram* dprog, int nd, const double* x, int64_t n, const double* diag_add,
+                          double* out, int64_t ld, cudaStream_t s);
+
+constexpr int DN_NB = 64;  // panel width
+
+// ---- diagonal block Cholesky (NB x NB) in shared memory; info != 0 when a pivot is not positive ------------------
+__global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ A, int64_t lda, int nb, int* info, int k0) {
+  __shared__ double s[DN_NB][DN_NB + 1];
+  for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) {
+    const int i = t % nb, j = t / nb;
+    s[i][j] = A[(int64_t)j * lda + i];
+  }
+  __syncthreads();
+  for (int k = 0; k < nb; ++k) {
+    const double d = s[k][k];
+    if (!(d > 0.0)) {  // also catches NaN; LAPACK's dpotrf info = k+1 (scipy raises LinAlgError)
+      if (threadIdx.x == 0 && atomicCAS(info, 0, k0 + k + 1) == 0) {}
+      return;
+    }
+    const double l = sqrt(d);
+    __syncthreads();
+    if (threadIdx.x == 0) s[k][k] = l;
+    for (int i = k + 1 + threadIdx.x; i < nb; i += blockDim.x) s[i][k] /= l;
+    __syncthreads();
+    const int rem = nb - k - 1;
+    for (int t = threadIdx.x; t < rem * rem; t += blockDim.x) {
+      const int i = k + 1 + t % rem, j = k + 1 + t / rem;
+      if (i >= j) s[i][j] -= s[i][k] * s[j][k];
+    }
+    __syncthreads();
+  }
+  for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) {
+    const int i = t % nb, j = t / nb;
+    A[(int64_t)j * lda + i] = (i >= j) ? s[i][j] : 0.0;  // explicit zeros above the diagonal of the block
+  }
+}
+
+// ---- panel solve: rows below the diagonal block, L21 = A21 * L11^-T; one row per thread ---------------------------
+__global__ void __launch_bounds__(128) trsm_panel_kernel(double* __restrict__ A, int64_t lda, int64_t rows, int nb,
+                                                         const int* info) {
+  __shared__ double l[DN_NB][DN_NB + 1];
+  if (*info != 0) return;
+  for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) {
+    const int i = t % nb, j = t / nb;
+    l[i][j] = A[(int64_t)j * lda + i];
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  double* row = A + nb + i;  // element (nb + i, j) at row[j*lda]
+  double w[DN_NB];
+#pragma unroll
+  for (int j = 0; j < DN_NB; ++j) w[j] = (j < nb) ? row[(int64_t)j * lda] : 0.0;
+#pragma unroll
+  for (int j = 0; j < DN_NB; ++j) {
+    if (j < nb) {
+      double s = w[j];
+#pragma unroll
+      for (int q = 0; q < j; ++q) s -= w[q] * l[j][q];
+      w[j] = s / l[j][j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < DN_NB; ++j)
+    if (j < nb) row[(int64_t)j * lda] = w[j];
+}
+
+// ---- generic column-major tile GEMM:  C (M x N) -= op(A) * op(B)   -------------------------------------------------
+//   TA == 0: A is M x K (lda), element (i,k) = A[k*lda + i];   TA == 1: A is K x M, element (i,k) = A[i*lda + k]
+//   TB == 0: B is K x N (ldb), element (k,j) = B[j*ldb + k];   TB == 1: B is N x K, element (k,j) = B[k*ldb + j]
+//   lower != 0: only tiles with i-tile >= j-tile are computed (SYRK-style trailing update)
+constexpr int GM_T = 64, GM_K = 16;
+template <int TA, int TB>
+__global__ void __launch_bounds__(256) gemm_sub_kernel(int64_t M, int64_t N, int K, const double* __restrict__ A,
+                                                       int64_t lda, const double* __restrict__ B, int64_t ldb,
+                                                       double* __restrict__ C, int64_t ldc, int lower,
+                                                       const int* info) {
+  if (info && *info != 0) return;
+  if (lower && blockIdx.x < blockIdx.y) return;
+  __shared__ double sa[GM_K][GM_T + 4];
+  __shared__ double sb[GM_K][GM_T + 4];
+  const int64_t i0 = (int64_t)blockIdx.x * GM_T, j0 = (int64_t)blockIdx.y * GM_T;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4x4 outputs each
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  for (int k0 = 0; k0 < K; k0 += GM_K) {
+    for (int t = threadIdx.x; t < GM_T * GM_K; t += 256) {
+      int i, k;
+      if (TA == 0) { i = t % GM_T; k = t / GM_T; } else { k = t % GM_K; i = t / GM_K; }
+      const int64_t gi = i0 + i;
+      const int gk = k0 + k;
+      double v = 0.0;
+      if (gi < M && gk < K) v = (TA == 0) ? A[(int64_t)gk * lda + gi] : A[gi * lda + gk];
+      sa[k][i] = v;
+    }
+    for (int t = threadIdx.x; t < GM_T * GM_K; t += 256) {
+      int j, k;
+      if (TB == 1) { j = t % GM_T; k = t / GM_T; } else { k = t % GM_K; j = t / GM_K; }
+      const int64_t gj = j0 + j;
+      const int gk = k0 + k;
+      double v = 0.0;
+      if (gj < N && gk < K) v = (TB == 1) ? B[(int64_t)gk * ldb + gj] : B[gj * ldb + gk];
+      sb[k][j] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GM_K; ++k) {
+      double a[4], b[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { a[e] = sa[k][tx + 16 * e]; b[e] = sb[k][ty + 16 * e]; }
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) acc[e][f] += a[e] * b[f];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int f = 0; f < 4; ++f)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int64_t gi = i0 + tx + 16 * e, gj = j0 + ty + 16 * f;
+      if (gi < M && gj < N && (!lower || gi >= gj)) C[gj * ldc + gi] -= acc[e][f];
+    }
+}
+
+// ---- triangular solves with the diagonal block for a slab of right-hand sides --------------------------------------
+// forward: X_k <- L_kk^-1 X_k ; backward: X_k <- L_kk^-T X_k.  One thread per RHS column; L_kk in shared memory.
+__global__ void __launch_bounds__(128) trsv_block_kernel(const double* __restrict__ L, int64_t ldl, int nb,
+                                                         double* __restrict__ X, int64_t ldx, int64_t nrhs,
+                                                         int backward) {
+  __shared__ double l[DN_NB][DN_NB + 1];
+  for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) {
+    const int i = t % nb, j = t / nb;
+    l[i][j] = L[(int64_t)j * ldl + i];
+  }
+  __syncthreads();
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nrhs) return;
+  double* x = X + c * ldx;
+  double w[DN_NB];
+#pragma unroll
+  for (int j = 0; j < DN_NB; ++j) w[j] = (j < nb) ? x[j] : 0.0;
+  if (!backward) {
+#pragma unroll
+    for (int j = 0; j < DN_NB; ++j)
+      if (j < nb) {
+        double s = w[j];
+#pragma unroll
+        for (int q = 0; q < j; ++q) s -= l[j][q] * w[q];
+        w[j] = s / l[j][j];
+      }
+  } else {
+#pragma unroll
+    for (int j = DN_NB - 1; j >= 0; --j)
+      if (j < nb) {
+        double s = w[j];
+#pragma unroll
+        for (int q = j + 1; q < DN_NB; ++q)
+          if (q < nb) s -= l[q][j] * w[q];
+        w[j] = s / l[j][j];
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < DN_NB; ++j)
+    if (j < nb) x[j] = w[j];
+}
+
+__global__ void logdet_diag_kernel(const double* __restrict__ A, int64_t lda, int64_t n, double* out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += log(A[i * lda + i]);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) *out = 2.0 * s;
+}
+__global__ void dot2_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    s += a[i] * b[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+__global__ void square2_kernel(const double* __restrict__ yerr, double* __restrict__ diag, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    diag[i] = yerr[i] * yerr[i];
+}
+// out (nr x n, row-major) = r (nr x n, row-major) @ U with U = L^T:  out[a][j] = sum_{i<=j} r[a][i] L[j][i]
+__global__ void apply_sqrt_kernel(const double* __restrict__ L, int64_t n, const double* __restrict__ r, int64_t nr,
+                                  double* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t a = blockIdx.y;
+  if (j >= n) return;
+  double s = 0.0;
+  for (int64_t i = 0; i <= j; ++i) s += r[a * n + i] * L[i * n + j];  // L[j][i] column-major = L[i*n + j]
+  out[a * n + j] = s;
+}
+
+}  // namespace bgp
+
+using namespace bgp;
+
+struct bgp_dense {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev[4] = {nullptr};
+  int64_t n = 0;
+  bool computed = false;
+  double log_det = 0.0;
+  DevBuf<DevProgram> d_prog;
+  DevBuf<double> d_x, d_yerr, d_diag, d_A, d_rhs, d_scalar;
+  DevBuf<int> d_info;
+  double t_ms[2] = {0, 0};
+};
+
+static int dense_potrf(bgp_dense* h) {
+  const int64_t n = h->n;
+  double* A = h->d_A.p;
+  cudaStream_t s = h->s;
+  for (int64_t k0 = 0; k0 < n; k0 += DN_NB) {
+    const int nb = (int)std::min<int64_t>(DN_NB, n - k0);
+    double* Akk = A + k0 * n + k0;
+    potf2_kernel<<<1, 256, 0, s>>>(Akk, n, nb, h->d_info.p, (int)k0);
+    BGP_LAUNCH_CHECK();
+    const int64_t rem = n - k0 - nb;
+    if (rem <= 0) break;
+    trsm_panel_kernel<<<(unsigned)((rem + 127) / 128), 128, 0, s>>>(Akk, n, rem, nb, h->d_info.p);
+    BGP_LAUNCH_CHECK();
+    const unsigned nt = (unsigned)((rem + GM_T - 1) / GM_T);
+    dim3 grid(nt, nt);
+    const double* A21 = Akk + nb;
+    gemm_sub_kernel<0, 1><<<grid, 256, 0, s>>>(rem, rem, nb, A21, n, A21, n, Akk + (int64_t)nb * n + nb, n, 1, h->d_info.p);
+    BGP_LAUNCH_CHECK();
+  }
+  return BGP_OK;
+}
+
+// X (n x nrhs, column-major ldx) <- K^-1 X on the device
+static int dense_potrs_dev(bgp_dense* h, double* X, int64_t nrhs, int64_t ldx) {
+  const int64_t n = h->n;
+  const double* L = h->d_A.p;
+  cudaStream_t s = h->s;
+  const unsigned cb = (unsigned)((nrhs + 127) / 128);
+  for (int64_t k0 = 0; k0 < n; k0 += DN_NB) {  // forward: L y = b
+    const int nb = (int)std::min<int64_t>(DN_NB, n - k0);
+    trsv_block_kernel<<<cb, 128, 0, s>>>(L + k0 * n + k0, n, nb, X + k0, ldx, nrhs, 0);
+    BGP_LAUNCH_CHECK();
+    const int64_t rem = n - k0 - nb;
+    if (rem <= 0) break;
+    dim3 grid((unsigned)((rem + GM_T - 1) / GM_T), (unsigned)((nrhs + GM_T - 1) / GM_T));
+    gemm_sub_kernel<0, 0><<<grid, 256, 0, s>>>(rem, nrhs, nb, L + k0 * n + k0 + nb, n, X + k0, ldx, X + k0 + nb, ldx, 0, nullptr);
+    BGP_LAUNCH_CHECK();
+  }
+  const int64_t last = ((n - 1) / DN_NB) * DN_NB;
+  for (int64_t k0 = last; k0 >= 0; k0 -= DN_NB) {  // backward: L^T x = y
+    const int nb = (int)std::min<int64_t>(DN_NB, n - k0);
+    trsv_block_kernel<<<cb, 128, 0, s>>>(L + k0 * n + k0, n, nb, X + k0, ldx, nrhs, 1);
+    BGP_LAUNCH_CHECK();
+    if (k0 == 0) break;
+    // X[0:k0] -= L[k0:k0+nb, 0:k0]^T X[k0:k0+nb]
+    dim3 grid((unsigned)((k0 + GM_T - 1) / GM_T), (unsigned)((nrhs + GM_T - 1) / GM_T));
+    gemm_sub_kernel<1, 0><<<grid, 256, 0, s>>>(k0, nrhs, nb, L + k0, n, X + k0, ldx, X, ldx, 0, nullptr);
+    BGP_LAUNCH_CHECK();
+  }
+  return BGP_OK;
+}
+
+extern "C" {
+
+int bgp_dense_create(bgp_dense_t** out) {
+  *out = new (std::nothrow) bgp_dense();
+  if (!*out) { set_error("out of host memory"); return BGP_ERR_NOMEM; }
+  return BGP_OK;
+}
+
+void bgp_dense_destroy(bgp_dense_t* h) {
+  if (!h) return;
+  if (h->s) cudaStreamSynchronize(h->s);
+  h->d_prog.release(); h->d_x.release(); h->d_yerr.release(); h->d_diag.release(); h->d_A.release();
+  h->d_rhs.release(); h->d_scalar.release(); h->d_info.release();
+  if (h->s) {
+    cudaStreamSynchronize(h->s);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(h->ev[i]);
+    cudaStreamDestroy(h->s);
+  }
+  delete h;
+}
+
+int bgp_dense_compute(bgp_dense_t* h, const bgp_kernel_spec_t* spec, const double* x, int64_t n, int32_t ndim,
+                      const double* yerr) {
+  if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
+  h->computed = false;
+  BGP_TRY(require_device());
+  if (!h->s) {
+    BGP_CUDA(cudaStreamCreateWithFlags(&h->s, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) BGP_CUDA(cudaEventCreate(&h->ev[i]));
+  }
+  DevProgram P;
+  BGP_TRY(build_dev_program(spec, &P));
+  if (P.ndim != ndim) { set_error("dimension mismatch: kernel ndim %d, input ndim %d", P.ndim, ndim); return BGP_ERR_DIM; }
+  if (n <= 0) { set_error("invalid number of points"); return BGP_ERR_INVALID; }
+  cudaStream_t s = h->s;
+  h->n = n;
+  BGP_TRY(upload_program(P, h->d_prog, s));
+  BGP_TRY(h->d_x.reserve((size_t)n * ndim, s));
+  BGP_TRY(h->d_yerr.reserve((size_t)n, s));
+  BGP_TRY(h->d_diag.reserve((size_t)n, s));
+  BGP_TRY(h->d_A.reserve((size_t)n * n, s));
+  BGP_TRY(h->d_info.reserve(1, s));
+  BGP_TRY(h->d_scalar.reserve(2, s));
+  BGP_CUDA(cudaMemcpyAsync(h->d_x.p, x, sizeof(double) * n * ndim, cudaMemcpyHostToDevice, s));
+  BGP_CUDA(cudaMemcpyAsync(h->d_yerr.p, yerr, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+  BGP_CUDA(cudaMemsetAsync(h->d_info.p, 0, sizeof(int), s));
+  square2_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, s>>>(h->d_yerr.p, h->d_diag.p, n);
+  BGP_LAUNCH_CHECK();
+  BGP_CUDA(cudaEventRecord(h->ev[0], s));
+  BGP_TRY(kmat_symmetric_launch(h->d_prog.p, ndim, h->d_x.p, n, h->d_diag.p, h->d_A.p, n, s));
+  BGP_CUDA(cudaEventRecord(h->ev[1], s));
+  BGP_TRY(dense_potrf(h));
+  logdet_diag_kernel<<<1, 1024, 0, s>>>(h->d_A.p, n, n, h->d_scalar.p);
+  BGP_LAUNCH_CHECK();
+  BGP_CUDA(cudaEventRecord(h->ev[2], s));
+  int info = 0;
+  double ld = 0.0;
+  BGP_CUDA(cudaMemcpyAsync(&info, h->d_info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  BGP_CUDA(cudaMemcpyAsync(&ld, h->d_scalar.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+  BGP_CUDA(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->t_ms[0] = ms;
+  cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->t_ms[1] = ms;
+  if (info != 0) {
+    set_error("%d-th leading minor of the array is not positive definite", info);
+    return BGP_ERR_LINALG;
+  }
+  h->log_det = ld;
+  h->computed = true;
+  return BGP_OK;
+}
+
+int bgp_dense_computed(const bgp_dense_t* h) { return h && h->computed ? 1 : 0; }
+
+int bgp_dense_log_determinant(const bgp_dense_t* h, double* out) {
+  if (!h || !h->computed) { set_error("the solver has not been computed"); return BGP_ERR_NOT_COMPUTED; }
+  *out = h->log_det;
+  return BGP_OK;
+}
+
+int bgp_dense_apply_inverse(bgp_dense_t* h, double* b, int64_t nrhs, int64_t ldb) {
+  if (!h || !h->computed) { set_error("the solver has not been computed"); return BGP_ERR_NOT_COMPUTED; }
+  if (nrhs <= 0) return BGP_OK;
+  if (ldb < h->n) { set_error("dimension mismatch: ldb < n"); return BGP_ERR_DIM; }
+  const int64_t n = h->n;
+  cudaStream_t s = h->s;
+  const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(nrhs, (int64_t)(1ull << 28) / n));
+  BGP_TRY(h->d_rhs.reserve((size_t)n * slab, s));
+  for (int64_t c0 = 0; c0 < nrhs; c0 += slab) {
+    const int64_t nc = std::min(slab, nrhs - c0);
+    BGP_CUDA(cudaMemcpy2DAsync(h->d_rhs.p, sizeof(double) * n, b + c0 * ldb, sizeof(double) * ldb, sizeof(double) * n, nc, cudaMemcpyHostToDevice, s));
+    BGP_TRY(dense_potrs_dev(h, h->d_rhs.p, nc, n));
+    BGP_CUDA(cudaMemcpy2DAsync(b + c0 * ldb, sizeof(double) * ldb, h->d_rhs.p, sizeof(double) * n, sizeof(double) * n, nc, cudaMemcpyDeviceToHost, s));
+    BGP_CUDA(cudaStreamSynchronize(s));
+  }
+  return BGP_OK;
+}
+
+int bgp_dense_dot_solve(bgp_dense_t* h, const double* y, double* out) {
+  if (!h || !h->computed) { set_error("the solver has not been computed"); return BGP_ERR_NOT_COMPUTED; }
+  const int64_t n = h->n;
+  cudaStream_t s = h->s;
+  BGP_TRY(h->d_rhs.reserve((size_t)n * 2, s));
+  double* yd = h->d_rhs.p;
+  double* xd = h->d_rhs.p + n;
+  BGP_CUDA(cudaMemcpyAsync(yd, y, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+  BGP_CUDA(cudaMemcpyAsync(xd, yd, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+  BGP_TRY(dense_potrs_dev(h, xd, 1, n));
+  BGP_CUDA(cudaMemsetAsync(h->d_scalar.p + 1, 0, sizeof(double), s));
+  dot2_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 592), 256, 0, s>>>(yd, xd, n, h->d_scalar.p + 1);
+  BGP_LAUNCH_CHECK();
+  BGP_CUDA(cudaMemcpyAsync(out, h->d_scalar.p + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+  BGP_CUDA(cudaStreamSynchronize(s));
+  return BGP_OK;
+}
+
+int bgp_dense_apply_sqrt(bgp_dense_t* h, const double* r, int64_t nr, double* out) {
+  if (!h || !h->computed) { set_error("the solver has not been computed"); return BGP_ERR_NOT_COMPUTED; }
+  const int64_t n = h->n;
+  cudaStream_t s = h->s;
+  if (nr <= 0) return BGP_OK;
+  DevBuf<double> dr, dout;
+  BGP_TRY(dr.alloc((size_t)nr * n, s));
+  BGP_TRY(dout.alloc((size_t)nr * n, s));
+  BGP_CUDA(cudaMemcpyAsync(dr.p, r, sizeof(double) * nr * n, cudaMemcpyHostToDevice, s));
+  dim3 grid((unsigned)((n + 127) / 128), (unsigned)nr);
+  apply_sqrt_kernel<<<grid, 128, 0, s>>>(h->d_A.p, n, dr.p, nr, dout.p);
+  BGP_LAUNCH_CHECK();
+  BGP_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * nr * n, cudaMemcpyDeviceToHost, s));
+  BGP_CUDA(cudaStreamSynchronize(s));
+  return BGP_OK;
+}
+
+int bgp_dense_get_inverse(bgp_dense_t* h, double* out) {
+  if (!h || !h->computed) { set_error("the solver has not been computed"); return BGP_ERR_NOT_COMPUTED; }
+  const int64_t n = h->n;
+  for (int64_t j = 0; j < n; ++j) {
+    double* c = out + j * n;
+    memset(c, 0, sizeof(double) * n);
+    c[j] = 1.0;
+  }
+  return bgp_dense_apply_inverse(h, out, n, n);
+}
+
+int bgp_dense_export_factor(bgp_dense_t* h, double* out) {
+  if (!h || !h->computed) { set_error("the solver has not been computed"); return BGP_ERR_NOT_COMPUTED; }
+  const int64_t n = h->n;
+  BGP_CUDA(cudaMemcpyAsync(out, h->d_A.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, h->s));
+  BGP_CUDA(cudaStreamSynchronize(h->s));
+  for (int64_t j = 1; j < n; ++j)
+    for (int64_t i = 0; i < j; ++i) out[j * n + i] = 0.0;  // column-major: element (i, j) with i < j
+  return BGP_OK;
+}
+
+int bgp_dense_import_factor(bgp_dense_t* h, const double* factor, int64_t n, double log_det) {
+  if (!h || n <= 0) { set_error("invalid argument"); return BGP_ERR_INVALID; }
+  h->computed = false;
+  BGP_TRY(require_device());
+  if (!h->s) {
+    BGP_CUDA(cudaStreamCreateWithFlags(&h->s, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) BGP_CUDA(cudaEventCreate(&h->ev[i]));
+  }
+  h->n = n;
+  BGP_TRY(h->d_A.reserve((size_t)n * n, h->s));
+  BGP_TRY(h->d_scalar.reserve(2, h->s));
+  BGP_CUDA(cudaMemcpyAsync(h->d_A.p, factor, sizeof(double) * n * n, cudaMemcpyHostToDevice, h->s));
+  BGP_CUDA(cudaStreamSynchronize(h->s));
+  h->log_det = log_det;
+  h->computed = true;
+  return BGP_OK;
+}
+
+int bgp_dense_last_timing(const bgp_dense_t* h, double* ms2) {
+  if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
+  ms2[0] = h->t_ms[0]; ms2[1] = h->t_ms[1];
+  return BGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,704 @@
+// hodlr.cu — host orchestration + C ABI of the HODLR solver (replaces src/george/solvers/_hodlr.cpp:36-204 and
+// the hodlr::Node recursion of src/george/include/george/hodlr.h).
+//
+// Pipeline of one compute() (all on the device; the host only builds the O(#nodes) index structure):
+//   tree geometry (host, bit-exact with hodlr.h:48-61)
+//   -> [stream A] leaf build + LDL^T (K4)      [stream B] ACA of every internal node (K5)
+//   -> ranks back to the host (one small D2H), per-level common ranks, panel finalisation
+//   -> leaf solves applied to all ancestor columns, then per level bottom-up: gram (K6a) -> LU/solve (K6b) -> update (K6c)
+//   -> log-det = sum of leaf and node log-dets.
+// solve(): the same three kernels with the right-hand side as target (K7).
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "hodlr_kernels.cuh"
+#include "kernel_eval.cuh"
+
+namespace bgp {
+int upload_program(const DevProgram& P, DevBuf<DevProgram>& buf, cudaStream_t s);
+}
+using namespace bgp;
+
+struct HNode {
+  int start, size, half, is_leaf, parent, dir, depth;
+  int slot;        // index within its level (internal) or within the leaf list
+  int rank = 0, draws = 0, fallback = 0;
+  int owned = 1;   // sharding: this process factors the node locally
+  int top = 0;     // sharding: node above the shard cut (finished after the exchange)
+};
+
+struct LevelInfo {
+  std::vector<int> nodes;  // pre-order ids of the internal nodes at this depth handled here
+  int cap = 0, max_cap = 0, vcol = 0, r = 0, ucol = 0;
+  int max_half = 0, grow = 0;
+  int desc_off = 0;  // offset of this level's NodeDesc block
+};
+
+struct bgp_hodlr {
+  cudaStream_t sA = nullptr, sB = nullptr;
+  cudaEvent_t ev[8] = {nullptr};
+  int64_t n = 0;
+  int ndim = 0;
+  bgp_hodlr_opts_t opts;
+  bool computed = false;
+  double log_det = 0.0;
+  DevProgram prog;
+
+  std::vector<HNode> nodes;  // pre-order
+  std::vector<int> leaves;   // pre-order ids
+  std::vector<LevelInfo> levels;
+  std::vector<int> piv_off;  // per internal node (by pre-order id) offset into pivot arrays, -1 for leaves
+  std::vector<int> h_piv_rows, h_piv_cols;
+  int max_leaf = 0, rtot = 0, vcols = 0, cut_depth = 0;
+  int64_t row0 = 0, nloc = 0;
+  std::vector<int64_t> shard_row0, shard_rows;
+
+  DevBuf<DevProgram> d_prog;
+  DevBuf<double> d_x, d_yerr, d_diag, d_L, d_leaf_logdet, d_node_logdet, d_V, d_U, d_S, d_W, d_scalar, d_rhs;
+  DevBuf<LeafDesc> d_leaves;
+  DevBuf<AcaDesc> d_aca;
+  DevBuf<AcaOut> d_aca_out;
+  DevBuf<NodeDesc> d_nodes;
+  DevBuf<int> d_idx, d_piv_rows, d_piv_cols, d_ticket, d_chain_done, d_ncols_by_depth;
+  DevBuf<uint32_t> d_chain_state;
+  size_t w_cap = 0;
+
+  double t_ms[5] = {0, 0, 0, 0, 0};
+  double work[6] = {0, 0, 0, 0, 0, 0};
+};
+
+static int ensure_streams(bgp_hodlr* h) {
+  if (!h->sA) {
+    BGP_CUDA(cudaStreamCreateWithFlags(&h->sA, cudaStreamNonBlocking));
+    BGP_CUDA(cudaStreamCreateWithFlags(&h->sB, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) BGP_CUDA(cudaEventCreate(&h->ev[i]));
+  }
+  return BGP_OK;
+}
+
+// hodlr.h:29-66: pre-order construction; a node splits iff size/2 >= min_size.
+static void build_tree(bgp_hodlr* h, int start, int size, int dir, int parent, int depth) {
+  HNode nd;
+  nd.start = start; nd.size = size; nd.half = size / 2; nd.dir = dir; nd.parent = parent; nd.depth = depth;
+  nd.is_leaf = !(nd.half >= h->opts.min_size);
+  nd.slot = 0;
+  const int id = (int)h->nodes.size();
+  h->nodes.push_back(nd);
+  if (!nd.is_leaf) {
+    build_tree(h, start, nd.half, 0, id, depth + 1);
+    build_tree(h, start + nd.half, size - nd.half, 1, id, depth + 1);
+  }
+}
+
+static int hodlr_solve_dev(bgp_hodlr* h, double* b, int64_t nrhs, int64_t ldb, cudaStream_t s, int part);
+
+static int launch_leaf_solve(bgp_hodlr* h, double* X, int64_t ldx, const int* ncols_by_depth, int ncols_fixed,
+                             int max_cols, cudaStream_t s) {
+  const int nl = (int)h->leaves.size();
+  if (nl == 0 || max_cols == 0) return BGP_OK;
+  // only leaves handled locally are in d_leaves
+  dim3 grid(nl, (max_cols + LS_COLS - 1) / LS_COLS);
+  const size_t smem = sizeof(double) * (size_t)h->max_leaf * LS_COLS;
+  if (smem > 200 * 1024) { set_error("leaf size %d too large for the leaf solve kernel", h->max_leaf); return BGP_ERR_INVALID; }
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(leaf_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  leaf_solve_kernel<<<grid, LS_THREADS, smem, s>>>(h->d_leaves.p, h->d_L.p, X, ldx, ncols_by_depth, ncols_fixed, h->max_leaf);
+  BGP_LAUNCH_CHECK();
+  return BGP_OK;
+}
+
+// one internal level: W = V^T X (both halves), small solve, X -= U T.   factor: up-sweep (X = U panel) vs plain solve
+static int launch_level(bgp_hodlr* h, const LevelInfo& L, double* X, int64_t ldx, int ncolsW, int own_off, int factor,
+                        int col_lo, int col_hi, cudaStream_t s) {
+  const int nn = (int)L.nodes.size();
+  if (nn == 0 || L.r == 0) {
+    return BGP_OK;
+  }
+  const int r = L.r;
+  const int64_t stride = (int64_t)r * ncolsW;
+  const size_t need = (size_t)nn * 2 * stride;
+  if (need > h->w_cap) { set_error("internal: W workspace too small (%zu > %zu)", need, h->w_cap); return BGP_ERR_CUDA; }
+  BGP_CUDA(cudaMemsetAsync(h->d_W.p, 0, sizeof(double) * need, s));
+  const NodeDesc* nd = h->d_nodes.p + L.desc_off;
+  const int max_nh = L.max_half + 1;
+  {
+    dim3 grid((max_nh + GT_CHUNK - 1) / GT_CHUNK, nn * 2, (ncolsW + GT_TC - 1) / GT_TC);
+    gram_tn_kernel<<<grid, GT_THREADS, 0, s>>>(nd, h->d_V.p, h->n, X, ldx, ncolsW, h->d_W.p, stride);
+    BGP_LAUNCH_CHECK();
+  }
+  {
+    const size_t sbytes = sizeof(double) * (size_t)(2 * r) * (2 * r);
+    const int in_smem = sbytes <= 160 * 1024;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(small_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
+    small_solve_kernel<<<nn, SS_THREADS, in_smem ? sbytes : 0, s>>>(nd, h->d_W.p, stride, ncolsW, own_off, factor, h->d_S.p,
+                                                                    h->d_node_logdet.p, L.desc_off, in_smem);
+    BGP_LAUNCH_CHECK();
+  }
+  if (col_hi > col_lo) {
+    dim3 grid((max_nh + UP_ROWS - 1) / UP_ROWS, nn * 2, (col_hi - col_lo + UP_TC - 1) / UP_TC);
+    update_nn_kernel<<<grid, UP_THREADS, 0, s>>>(nd, h->d_U.p, h->n, X, ldx, col_lo, col_hi, h->d_W.p, stride, 0);
+    BGP_LAUNCH_CHECK();
+  }
+  return BGP_OK;
+}
+
+static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, const double* x_dev, int64_t n,
+                                  int32_t ndim, const double* yerr_dev, const bgp_hodlr_opts_t* opts_in) {
+  h->computed = false;
+  BGP_TRY(require_device());
+  BGP_TRY(ensure_streams(h));
+  BGP_TRY(build_dev_program(spec, &h->prog));
+  if (h->prog.ndim != ndim) { set_error("dimension mismatch: kernel ndim %d, input ndim %d", h->prog.ndim, ndim); return BGP_ERR_DIM; }
+  if (ndim > ACA_MAX_NDIM) { set_error("HODLR supports at most %d input dimensions", ACA_MAX_NDIM); return BGP_ERR_INVALID; }
+  if (n <= 0 || n > (int64_t)0x7fffffff) { set_error("invalid number of points %lld", (long long)n); return BGP_ERR_INVALID; }
+  bgp_hodlr_opts_t o;
+  if (opts_in) o = *opts_in; else bgp_hodlr_default_opts(&o);
+  if (o.min_size < 1) { set_error("min_size must be >= 1"); return BGP_ERR_INVALID; }
+  if (o.shard_count < 1) o.shard_count = 1;
+  if (o.shard_count & (o.shard_count - 1)) { set_error("shard_count must be a power of two"); return BGP_ERR_INVALID; }
+  if (o.shard_rank < 0 || o.shard_rank >= o.shard_count) { set_error("invalid shard_rank"); return BGP_ERR_INVALID; }
+  if (o.shard_count > 1 && o.rng_mode == BGP_RNG_REFERENCE) { set_error("rng_mode=reference serialises the tree and cannot be sharded"); return BGP_ERR_INVALID; }
+  h->opts = o;
+  h->n = n;
+  h->ndim = ndim;
+  cudaStream_t sA = h->sA, sB = h->sB;
+
+  // ---- tree geometry ----
+  h->nodes.clear(); h->leaves.clear(); h->levels.clear();
+  h->nodes.reserve(2 * (size_t)(n / std::max(1, o.min_size)) + 8);
+  build_tree(h, 0, (int)n, 0, -1, 0);
+  int cut = 0;
+  while ((1 << cut) < o.shard_count) cut++;
+  h->cut_depth = cut;
+  // sharding: the sub-tree owned by this process is the depth-`cut` node number shard_rank (left-to-right);
+  // if the tree is shallower than the cut, everything is "top" work done redundantly.
+  int max_depth = 0;
+  for (auto& nd : h->nodes) max_depth = std::max(max_depth, nd.depth);
+  h->row0 = 0; h->nloc = n;
+  if (o.shard_count > 1) {
+    int seen = 0; bool found = false;
+    h->shard_row0.clear(); h->shard_rows.clear();
+    for (size_t i = 0; i < h->nodes.size(); ++i) {
+      HNode& nd = h->nodes[i];
+      if (nd.depth == cut) {
+        if (seen == o.shard_rank) { h->row0 = nd.start; h->nloc = nd.size; found = true; }
+        h->shard_row0.push_back(nd.start); h->shard_rows.push_back(nd.size);
+        seen++;
+      }
+    }
+    if (!found || seen != o.shard_count) { set_error("tree too shallow to shard %d ways (N=%lld, min_size=%d)", o.shard_count, (long long)n, o.min_size); return BGP_ERR_INVALID; }
+    for (auto& nd : h->nodes) {
+      nd.top = nd.depth < cut;
+      nd.owned = !nd.top && nd.start >= h->row0 && nd.start + nd.size <= h->row0 + h->nloc;
+    }
+  }
+  h->levels.assign(max_depth + 1, LevelInfo());
+  for (size_t i = 0; i < h->nodes.size(); ++i) {
+    HNode& nd = h->nodes[i];
+    if (nd.is_leaf) { if (nd.owned) { nd.slot = (int)h->leaves.size(); h->leaves.push_back((int)i); } continue; }
+    if (!(nd.owned || nd.top)) continue;
+    LevelInfo& L = h->levels[nd.depth];
+    nd.slot = (int)L.nodes.size();
+    L.nodes.push_back((int)i);
+    L.max_half = std::max(L.max_half, nd.size - nd.half);
+  }
+  while (!h->levels.empty() && h->levels.back().nodes.empty()) h->levels.pop_back();
+  const int nlev = (int)h->levels.size();
+
+  // ---- capacities: start from rank_capacity (default 128) per level; levels that overflow are grown and the ACA
+  //      stage is repeated (deterministic: the per-node / chained streams restart from the same seeds) ----
+  const int rcap0 = o.rank_capacity > 0 ? o.rank_capacity : 128;
+  for (auto& L : h->levels) {
+    int mh = 0;
+    for (int id : L.nodes) mh = std::max(mh, h->nodes[id].half);
+    L.max_cap = std::max(1, mh);
+    L.cap = std::min(rcap0, L.max_cap);
+  }
+
+  // ---- inputs ----
+  BGP_TRY(upload_program(h->prog, h->d_prog, sA));
+  BGP_TRY(h->d_x.reserve((size_t)n * ndim, sA));
+  BGP_TRY(h->d_diag.reserve((size_t)n, sA));
+  if (x_dev != h->d_x.p) BGP_CUDA(cudaMemcpyAsync(h->d_x.p, x_dev, sizeof(double) * n * ndim, cudaMemcpyDeviceToDevice, sA));
+  square_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, sA>>>(yerr_dev, h->d_diag.p, n);
+  BGP_LAUNCH_CHECK();
+  BGP_CUDA(cudaEventRecord(h->ev[0], sA));  // inputs ready / timing origin
+
+  // ---- leaves (stream A) ----
+  const int nl = (int)h->leaves.size();
+  std::vector<LeafDesc> hleaves(nl);
+  int64_t loff = 0;
+  h->max_leaf = 0;
+  for (int i = 0; i < nl; ++i) {
+    const HNode& nd = h->nodes[h->leaves[i]];
+    hleaves[i].start = nd.start; hleaves[i].size = nd.size; hleaves[i].depth = nd.depth; hleaves[i]._pad = 0;
+    hleaves[i].off = loff;
+    loff += (int64_t)nd.size * nd.size;
+    h->max_leaf = std::max(h->max_leaf, nd.size);
+  }
+  BGP_TRY(h->d_leaves.reserve(std::max(nl, 1), sA));
+  BGP_TRY(h->d_L.reserve((size_t)std::max<int64_t>(loff, 1), sA));
+  BGP_TRY(h->d_leaf_logdet.reserve(std::max(nl, 1), sA));
+  if (nl) {
+    BGP_CUDA(cudaMemcpyAsync(h->d_leaves.p, hleaves.data(), sizeof(LeafDesc) * nl, cudaMemcpyHostToDevice, sA));
+    leaf_build_factor_kernel<<<nl, LEAF_THREADS, 0, sA>>>(h->d_prog.p, h->d_x.p, h->d_diag.p, h->d_leaves.p, h->d_L.p,
+                                                          h->d_leaf_logdet.p);
+    BGP_LAUNCH_CHECK();
+  }
+  BGP_CUDA(cudaEventRecord(h->ev[1], sA));  // leaves done
+
+  // ---- ACA (stream B, concurrent with the leaves) ----
+  std::vector<AcaDesc> hdesc;
+  std::vector<int> desc_node;  // pre-order id per descriptor
+  std::vector<AcaOut> houts;
+  int64_t idx_total = 0, piv_total = 0;
+  int nint = 0;
+  BGP_CUDA(cudaStreamWaitEvent(sB, h->ev[0], 0));
+  for (int attempt = 0;; ++attempt) {
+    int vcols = 0;
+    for (auto& L : h->levels) { L.vcol = vcols; vcols += L.cap; }
+    h->vcols = vcols;
+    hdesc.clear(); desc_node.clear();
+    h->piv_off.assign(h->nodes.size(), -1);
+    idx_total = 0; piv_total = 0; nint = 0;
+    for (int l = 0; l < nlev; ++l) {
+      for (int id : h->levels[l].nodes) {
+        const HNode& nd = h->nodes[id];
+        AcaDesc d;
+        d.row0 = nd.start + nd.half; d.n_rows = nd.size - nd.half; d.col0 = nd.start; d.n_cols = nd.half;
+        d.vcol = h->levels[l].vcol; d.cap = h->levels[l].cap; d.pre_id = id; d.node = nint;
+        d.idx_off = idx_total; d.piv_off = piv_total;
+        h->piv_off[id] = (int)piv_total;
+        idx_total += d.n_rows; piv_total += d.cap;
+        hdesc.push_back(d); desc_node.push_back(id);
+        nint++;
+      }
+    }
+    // launch order: pre-order for the chained reference stream, largest blocks first otherwise
+    std::vector<int> order(nint);
+    for (int i = 0; i < nint; ++i) order[i] = i;
+    if (o.rng_mode == BGP_RNG_REFERENCE) std::sort(order.begin(), order.end(), [&](int a, int b) { return hdesc[a].pre_id < hdesc[b].pre_id; });
+    else std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return hdesc[a].n_rows > hdesc[b].n_rows; });
+    std::vector<AcaDesc> hdesc_sorted(nint);
+    for (int i = 0; i < nint; ++i) hdesc_sorted[i] = hdesc[order[i]];
+
+    BGP_TRY(h->d_V.reserve((size_t)n * std::max(vcols, 1), sB));
+    BGP_TRY(h->d_aca.reserve(std::max(nint, 1), sB));
+    BGP_TRY(h->d_aca_out.reserve(std::max(nint, 1), sB));
+    BGP_TRY(h->d_idx.reserve((size_t)std::max<int64_t>(idx_total, 1), sB));
+    BGP_TRY(h->d_piv_rows.reserve((size_t)std::max<int64_t>(piv_total, 1), sB));
+    BGP_TRY(h->d_piv_cols.reserve((size_t)std::max<int64_t>(piv_total, 1), sB));
+    BGP_TRY(h->d_ticket.reserve(1, sB));
+    BGP_TRY(h->d_chain_state.reserve(640, sB));
+    BGP_TRY(h->d_chain_done.reserve(std::max(nint, 1), sB));
+    houts.assign(nint, AcaOut());
+    if (nint) {
+      BGP_CUDA(cudaMemcpyAsync(h->d_aca.p, hdesc_sorted.data(), sizeof(AcaDesc) * nint, cudaMemcpyHostToDevice, sB));
+      BGP_CUDA(cudaMemsetAsync(h->d_ticket.p, 0, sizeof(int), sB));
+      BGP_CUDA(cudaMemsetAsync(h->d_chain_done.p, 0, sizeof(int) * nint, sB));
+      int maxcap = 1;
+      for (auto& L : h->levels) maxcap = std::max(maxcap, L.cap);
+      const size_t smem = ((sizeof(AcaShared) + 15) & ~size_t(15)) + sizeof(double) * (size_t)maxcap;
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(aca_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+      if (smem > 200 * 1024) { set_error("rank capacity %d too large", maxcap); return BGP_ERR_RANK_CAPACITY; }
+      aca_kernel<<<nint, ACA_THREADS, smem, sB>>>(h->d_prog.p, h->d_x.p, h->d_aca.p, nint, h->d_V.p, n, o.tol, (uint32_t)o.seed,
+                                                  o.rng_mode, h->d_idx.p, h->d_piv_rows.p, h->d_piv_cols.p, h->d_aca_out.p,
+                                                  h->d_ticket.p, h->d_chain_state.p, h->d_chain_done.p, o.exhaust_mode);
+      BGP_LAUNCH_CHECK();
+      BGP_CUDA(cudaMemcpyAsync(houts.data(), h->d_aca_out.p, sizeof(AcaOut) * nint, cudaMemcpyDeviceToHost, sB));
+    }
+    BGP_CUDA(cudaEventRecord(h->ev[2], sB));  // ACA done
+    BGP_CUDA(cudaStreamSynchronize(sB));
+
+    // ---- ranks; grow the capacity of overflowing levels and repeat ----
+    bool overflow = false;
+    for (int i = 0; i < nint; ++i) {
+      HNode& nd = h->nodes[desc_node[i]];
+      nd.rank = houts[i].rank; nd.draws = houts[i].draws; nd.fallback = houts[i].fallback;
+      if (houts[i].status != 0) {
+        LevelInfo& L = h->levels[nd.depth];
+        if (o.rank_capacity > 0 || L.cap >= L.max_cap) {
+          set_error("ACA rank capacity exceeded at node [start=%d size=%d] (capacity %d%s); raise rank_capacity", nd.start,
+                    nd.size, L.cap, houts[i].fallback ? ", dense fallback" : "");
+          return BGP_ERR_RANK_CAPACITY;
+        }
+        L.grow = houts[i].fallback ? L.max_cap : std::max(L.grow, std::min(L.max_cap, 2 * L.cap));
+        overflow = true;
+      }
+    }
+    if (!overflow) break;
+    for (auto& L : h->levels) if (L.grow > L.cap) L.cap = L.grow;
+    if (attempt > 16) { set_error("ACA capacity growth did not converge"); return BGP_ERR_RANK_CAPACITY; }
+  }
+  int rtot = 0, ndesc = 0;
+  int64_t s_total = 0;
+  size_t w_need = 1;
+  std::vector<NodeDesc> hnd;
+  for (int l = 0; l < nlev; ++l) {
+    LevelInfo& L = h->levels[l];
+    L.r = 0;
+    for (int id : L.nodes) L.r = std::max(L.r, h->nodes[id].rank);
+    L.ucol = rtot;
+    rtot += L.r;
+    L.desc_off = ndesc;
+    for (int id : L.nodes) {
+      const HNode& nd = h->nodes[id];
+      NodeDesc d;
+      d.start = nd.start; d.size = nd.size; d.half = nd.half; d.depth = nd.depth; d.vcol = L.vcol; d.ucol = L.ucol;
+      d.r = L.r; d.rank = nd.rank; d.s_off = s_total;
+      s_total += (int64_t)(2 * L.r) * (2 * L.r) + 2 * L.r + 2;
+      hnd.push_back(d);
+      ndesc++;
+    }
+    w_need = std::max(w_need, (size_t)L.nodes.size() * 2 * (size_t)L.r * (size_t)(L.ucol + L.r));
+  }
+  h->rtot = rtot;
+  // per-depth number of ancestor columns a leaf (or node) at that depth sees
+  std::vector<int> ncols_by_depth(max_depth + 2, rtot);
+  for (int dpt = 0; dpt <= max_depth + 1; ++dpt) ncols_by_depth[dpt] = dpt < nlev ? h->levels[dpt].ucol : rtot;
+
+  BGP_TRY(h->d_nodes.reserve(std::max(ndesc, 1), sA));
+  BGP_TRY(h->d_node_logdet.reserve(std::max(ndesc, 1), sA));
+  BGP_TRY(h->d_U.reserve((size_t)n * std::max(rtot, 1), sA));
+  BGP_TRY(h->d_S.reserve((size_t)std::max<int64_t>(s_total, 1), sA));
+  // solve() needs 2*r*nrhs per node; keep room for 64 right-hand sides per batch
+  for (auto& L : h->levels) w_need = std::max(w_need, (size_t)L.nodes.size() * 2 * (size_t)L.r * 64);
+  BGP_TRY(h->d_W.reserve(w_need, sA));
+  h->w_cap = h->d_W.n;
+  BGP_TRY(h->d_ncols_by_depth.reserve(ncols_by_depth.size(), sA));
+  BGP_TRY(h->d_scalar.reserve(4, sA));
+  BGP_CUDA(cudaMemcpyAsync(h->d_ncols_by_depth.p, ncols_by_depth.data(), sizeof(int) * ncols_by_depth.size(), cudaMemcpyHostToDevice, sA));
+  if (ndesc) {
+    BGP_CUDA(cudaMemcpyAsync(h->d_nodes.p, hnd.data(), sizeof(NodeDesc) * ndesc, cudaMemcpyHostToDevice, sA));
+    BGP_CUDA(cudaMemsetAsync(h->d_node_logdet.p, 0, sizeof(double) * ndesc, sA));
+    int rmax = 0;
+    for (auto& L : h->levels) rmax = std::max(rmax, L.r);
+    if (rmax > 0) {
+      dim3 grid(ndesc, rmax);
+      finalize_panels_kernel<<<grid, 256, 0, sA>>>(h->d_nodes.p, h->d_V.p, n, h->d_U.p, n);
+      BGP_LAUNCH_CHECK();
+    }
+  }
+
+  // ---- up-sweep (stream A; leaves are already ordered before this on the same stream) ----
+  if (rtot > 0) BGP_TRY(launch_leaf_solve(h, h->d_U.p, n, h->d_ncols_by_depth.p, 0, rtot, sA));
+  const int stop_level = (o.shard_count > 1) ? h->cut_depth : 0;
+  for (int l = nlev - 1; l >= stop_level; --l) {
+    const LevelInfo& L = h->levels[l];
+    BGP_TRY(launch_level(h, L, h->d_U.p, n, L.ucol + L.r, L.ucol, 1, 0, L.ucol, sA));
+  }
+  BGP_CUDA(cudaEventRecord(h->ev[3], sA));
+  if (o.shard_count > 1) {
+    // the caller exchanges the top panel rows and calls bgp_hodlr_finish_top()
+    BGP_CUDA(cudaStreamSynchronize(sA));
+    return BGP_OK;
+  }
+
+  // ---- log-det ----
+  std::vector<double> ld_leaf(nl), ld_node(ndesc);
+  if (nl) BGP_CUDA(cudaMemcpyAsync(ld_leaf.data(), h->d_leaf_logdet.p, sizeof(double) * nl, cudaMemcpyDeviceToHost, sA));
+  if (ndesc) BGP_CUDA(cudaMemcpyAsync(ld_node.data(), h->d_node_logdet.p, sizeof(double) * ndesc, cudaMemcpyDeviceToHost, sA));
+  if (nint) {
+    h->h_piv_rows.resize(piv_total); h->h_piv_cols.resize(piv_total);
+  }
+  BGP_CUDA(cudaStreamSynchronize(sA));
+  double ld = 0.0;
+  for (double v : ld_leaf) ld += v;
+  for (double v : ld_node) ld += v;
+  h->log_det = ld;
+  h->computed = true;
+
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->t_ms[0] = ms;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]); h->t_ms[1] = ms;
+  cudaEventElapsedTime(&ms, h->ev[1], h->ev[3]); h->t_ms[2] = ms;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]); h->t_ms[3] = ms;
+
+  // algorithmic work
+  {
+    double evals = 0, bytes = 0, flops = 0, R = rtot;
+    for (int id : h->leaves) { const double m = h->nodes[id].size; evals += m * (m + 1) / 2; bytes += 8 * m * m; flops += m * m * m / 3 + 2 * m * m * ncols_by_depth[h->nodes[id].depth]; }
+    for (int l = 0; l < nlev; ++l) {
+      const LevelInfo& L = h->levels[l];
+      for (int id : L.nodes) {
+        const HNode& nd = h->nodes[id];
+        evals += (double)nd.size * nd.draws;  // one row + one column of the block per accepted/rejected draw (upper bound)
+        bytes += 16.0 * nd.size * nd.rank;
+        flops += 4.0 * nd.size * L.r * L.ucol + 2.0 * nd.size * L.r * L.r + 2.0 * nd.size * nd.rank * nd.rank;
+      }
+    }
+    h->work[0] = evals; h->work[1] = bytes; h->work[2] = flops; h->work[3] = R; h->work[4] = h->max_leaf; h->work[5] = nlev;
+  }
+  return BGP_OK;
+}
+
+// part: 0 = everything, 1 = local (leaves + levels >= cut), 2 = top (levels < cut)
+static int hodlr_solve_dev(bgp_hodlr* h, double* b, int64_t nrhs, int64_t ldb, cudaStream_t s, int part) {
+  const int nlev = (int)h->levels.size();
+  const int cut = h->opts.shard_count > 1 ? h->cut_depth : 0;
+  for (int64_t c0 = 0; c0 < nrhs; c0 += 64) {
+    const int nc = (int)std::min<int64_t>(64, nrhs - c0);
+    double* X = b + c0 * ldb;
+    if (part != 2) {
+      BGP_TRY(launch_leaf_solve(h, X, ldb, nullptr, nc, nc, s));
+      for (int l = nlev - 1; l >= cut; --l) BGP_TRY(launch_level(h, h->levels[l], X, ldb, nc, 0, 0, 0, nc, s));
+    }
+    if (part != 1) {
+      for (int l = std::min(cut, nlev) - 1; l >= 0; --l) BGP_TRY(launch_level(h, h->levels[l], X, ldb, nc, 0, 0, 0, nc, s));
+    }
+  }
+  return BGP_OK;
+}
+
+extern "C" {
+
+void bgp_hodlr_default_opts(bgp_hodlr_opts_t* o) {
+  o->min_size = 100; o->seed = 42; o->tol = 0.1;  // _hodlr.cpp:202
+  o->rng_mode = BGP_RNG_PER_NODE; o->rank_capacity = 0; o->shard_rank = 0; o->shard_count = 1; o->exhaust_mode = BGP_EXHAUST_DENSE;
+}
+
+int bgp_hodlr_create(bgp_hodlr_t** out) {
+  *out = new (std::nothrow) bgp_hodlr();
+  if (!*out) { set_error("out of host memory"); return BGP_ERR_NOMEM; }
+  bgp_hodlr_default_opts(&(*out)->opts);
+  return BGP_OK;
+}
+
+void bgp_hodlr_destroy(bgp_hodlr_t* h) {
+  if (!h) return;
+  if (h->sA) {
+    cudaStreamSynchronize(h->sA); cudaStreamSynchronize(h->sB);
+  }
+  // release buffers while the streams are still alive
+  h->d_prog.release(); h->d_x.release(); h->d_yerr.release(); h->d_diag.release(); h->d_L.release();
+  h->d_leaf_logdet.release(); h->d_node_logdet.release(); h->d_V.release(); h->d_U.release(); h->d_S.release();
+  h->d_W.release(); h->d_scalar.release(); h->d_rhs.release(); h->d_leaves.release(); h->d_aca.release();
+  h->d_aca_out.release(); h->d_nodes.release(); h->d_idx.release(); h->d_piv_rows.release(); h->d_piv_cols.release();
+  h->d_ticket.release(); h->d_chain_done.release(); h->d_ncols_by_depth.release(); h->d_chain_state.release();
+  if (h->sA) {
+    cudaStreamSynchronize(h->sA); cudaStreamSynchronize(h->sB);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
+    cudaStreamDestroy(h->sA); cudaStreamDestroy(h->sB);
+  }
+  delete h;
+}
+
+int bgp_hodlr_compute_dev(bgp_hodlr_t* h, const bgp_kernel_spec_t* spec, const double* x_dev, int64_t n, int32_t ndim,
+                          const double* yerr_dev, const bgp_hodlr_opts_t* opts) {
+  if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
+  return hodlr_compute_dev_impl(h, spec, x_dev, n, ndim, yerr_dev, opts);
+}
+
+int bgp_hodlr_compute(bgp_hodlr_t* h, const bgp_kernel_spec_t* spec, const double* x, int64_t n, int32_t ndim,
+                      const double* yerr, const bgp_hodlr_opts_t* opts) {
+  if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
+  h->computed = false;
+  BGP_TRY(require_device());
+  BGP_TRY(ensure_streams(h));
+  if (n <= 0 || ndim <= 0) { set_error("invalid input shape (%lld, %d)", (long long)n, ndim); return BGP_ERR_INVALID; }
+  BGP_TRY(h->d_x.reserve((size_t)n * ndim, h->sA));
+  BGP_TRY(h->d_yerr.reserve((size_t)n, h->sA));
+  BGP_CUDA(cudaMemcpyAsync(h->d_x.p, x, sizeof(double) * n * ndim, cudaMemcpyHostToDevice, h->sA));
+  BGP_CUDA(cudaMemcpyAsync(h->d_yerr.p, yerr, sizeof(double) * n, cudaMemcpyHostToDevice, h->sA));
+  return hodlr_compute_dev_impl(h, spec, h->d_x.p, n, ndim, h->d_yerr.p, opts);
+}
+
+int bgp_hodlr_computed(const bgp_hodlr_t* h) { return h && h->computed ? 1 : 0; }
+
+int bgp_hodlr_log_determinant(const bgp_hodlr_t* h, double* out) {
+  if (!h || !h->computed) { set_error("the solver has not been computed"); return BGP_ERR_NOT_COMPUTED; }
+  *out = h->log_det;
+  return BGP_OK;
+}
+
+int bgp_hodlr_apply_inverse(bgp_hodlr_t* h, double* b, int64_t nrhs, int64_t ldb) {
+  if (!h || !h->computed) { set_error("the solver has not been computed"); return BGP_ERR_NOT_COMPUTED; }
+  if (nrhs <= 0) return BGP_OK;
+  if (ldb < h->n) { set_error("dimension mismatch: ldb < n"); return BGP_ERR_DIM; }
+  cudaStream_t s = h->sA;
+  const int64_t n = h->n;
+  // process in slabs of columns to bound device memory
+  const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(nrhs, (int64_t)(1ull << 28) / n));
+  BGP_TRY(h->d_rhs.reserve((size_t)n * slab, s));
+  for (int64_t c0 = 0; c0 < nrhs; c0 += slab) {
+    const int64_t nc = std::min(slab, nrhs - c0);
+    BGP_CUDA(cudaMemcpy2DAsync(h->d_rhs.p, sizeof(double) * n, b + c0 * ldb, sizeof(double) * ldb, sizeof(double) * n, nc, cudaMemcpyHostToDevice, s));
+    BGP_CUDA(cudaEventRecord(h->ev[4], s));
+    BGP_TRY(hodlr_solve_dev(h, h->d_rhs.p, nc, n, s, 0));
+    BGP_CUDA(cudaEventRecord(h->ev[5], s));
+    BGP_CUDA(cudaMemcpy2DAsync(b + c0 * ldb, sizeof(double) * ldb, h->d_rhs.p, sizeof(double) * n, sizeof(double) * n, nc, cudaMemcpyDeviceToHost, s));
+    BGP_CUDA(cudaStreamSynchronize(s));
+  }
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->t_ms[4] = ms;
+  return BGP_OK;
+}
+
+int bgp_hodlr_dot_solve_dev(bgp_hodlr_t* h, const double* y_dev, double* out) {
+  if (!h || !h->computed) { set_error("the solver has not been computed"); return BGP_ERR_NOT_COMPUTED; }
+  cudaStream_t s = h->sA;
+  const int64_t n = h->n;
+  BGP_TRY(h->d_rhs.reserve((size_t)n, s));
+  BGP_CUDA(cudaEventRecord(h->ev[4], s));
+  BGP_CUDA(cudaMemcpyAsync(h->d_rhs.p, y_dev, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+  BGP_TRY(hodlr_solve_dev(h, h->d_rhs.p, 1, n, s, 0));
+  BGP_CUDA(cudaMemsetAsync(h->d_scalar.p, 0, sizeof(double), s));
+  dot_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 592), 256, 0, s>>>(y_dev, h->d_rhs.p, n, h->d_scalar.p);
+  BGP_LAUNCH_CHECK();
+  BGP_CUDA(cudaEventRecord(h->ev[5], s));
+  BGP_CUDA(cudaMemcpyAsync(out, h->d_scalar.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+  BGP_CUDA(cudaStreamSynchronize(s));
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->t_ms[4] = ms;
+  return BGP_OK;
+}
+
+int bgp_hodlr_dot_solve(bgp_hodlr_t* h, const double* y, double* out) {
+  if (!h || !h->computed) { set_error("the solver has not been computed"); return BGP_ERR_NOT_COMPUTED; }
+  cudaStream_t s = h->sA;
+  BGP_TRY(h->d_yerr.reserve((size_t)h->n, s));  // reuse as staging for y
+  BGP_CUDA(cudaMemcpyAsync(h->d_yerr.p, y, sizeof(double) * h->n, cudaMemcpyHostToDevice, s));
+  return bgp_hodlr_dot_solve_dev(h, h->d_yerr.p, out);
+}
+
+int bgp_hodlr_get_inverse(bgp_hodlr_t* h, double* out) {
+  if (!h || !h->computed) { set_error("the solver has not been computed"); return BGP_ERR_NOT_COMPUTED; }
+  const int64_t n = h->n;
+  for (int64_t j = 0; j < n; ++j) {
+    double* c = out + j * n;
+    memset(c, 0, sizeof(double) * n);
+    c[j] = 1.0;
+  }
+  return bgp_hodlr_apply_inverse(h, out, n, n);  // symmetric: row-/column-major agree
+}
+
+int bgp_hodlr_num_nodes(const bgp_hodlr_t* h, int64_t* out) {
+  if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
+  *out = (int64_t)h->nodes.size();
+  return BGP_OK;
+}
+
+int bgp_hodlr_node_info(const bgp_hodlr_t* h, bgp_hodlr_node_info_t* out) {
+  if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
+  for (size_t i = 0; i < h->nodes.size(); ++i) {
+    const HNode& nd = h->nodes[i];
+    out[i].start = nd.start; out[i].size = nd.size; out[i].half = nd.half; out[i].is_leaf = nd.is_leaf;
+    out[i].parent = nd.parent; out[i].direction = nd.dir; out[i].depth = nd.depth; out[i].rank = nd.rank;
+    out[i].rng_draws = nd.draws; out[i].dense_fallback = nd.fallback;
+  }
+  return BGP_OK;
+}
+
+int bgp_hodlr_node_pivots(const bgp_hodlr_t* hc, int64_t node, int32_t* rows, int32_t* cols) {
+  bgp_hodlr_t* h = const_cast<bgp_hodlr_t*>(hc);
+  if (!h || node < 0 || node >= (int64_t)h->nodes.size()) { set_error("node index out of range"); return BGP_ERR_INDEX; }
+  const HNode& nd = h->nodes[node];
+  if (nd.is_leaf || h->piv_off[node] < 0 || nd.rank == 0 || nd.fallback) return BGP_OK;
+  BGP_CUDA(cudaMemcpy(rows, h->d_piv_rows.p + h->piv_off[node], sizeof(int) * nd.rank, cudaMemcpyDeviceToHost));
+  BGP_CUDA(cudaMemcpy(cols, h->d_piv_cols.p + h->piv_off[node], sizeof(int) * nd.rank, cudaMemcpyDeviceToHost));
+  return BGP_OK;
+}
+
+int bgp_hodlr_last_timing(const bgp_hodlr_t* h, double* ms5) {
+  if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
+  for (int i = 0; i < 5; ++i) ms5[i] = h->t_ms[i];
+  return BGP_OK;
+}
+int bgp_hodlr_last_work(const bgp_hodlr_t* h, double* w6) {
+  if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
+  for (int i = 0; i < 6; ++i) w6[i] = h->work[i];
+  return BGP_OK;
+}
+
+// ---- multi-GPU exchange -----------------------------------------------------------------------
+int bgp_hodlr_top_panel(bgp_hodlr_t* h, double** ptr_dev, int64_t* row0, int64_t* rows, int64_t* cols, int64_t* ld) {
+  if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
+  const int cut = std::min<int>(h->cut_depth, (int)h->levels.size());
+  *ptr_dev = h->d_U.p;
+  *row0 = h->row0; *rows = h->nloc;
+  *cols = cut < (int)h->levels.size() ? h->levels[cut].ucol : h->rtot;
+  *ld = h->n;
+  return BGP_OK;
+}
+
+static int64_t top_cols(const bgp_hodlr_t* h) {
+  const int cut = std::min<int>(h->cut_depth, (int)h->levels.size());
+  return cut < (int)h->levels.size() ? h->levels[cut].ucol : h->rtot;
+}
+
+int bgp_hodlr_shard_rows(const bgp_hodlr_t* h, int32_t s, int64_t* row0, int64_t* rows) {
+  if (!h || s < 0 || s >= (int)h->shard_rows.size()) { set_error("shard index out of range"); return BGP_ERR_INDEX; }
+  *row0 = h->shard_row0[s]; *rows = h->shard_rows[s];
+  return BGP_OK;
+}
+
+int bgp_hodlr_export_top(bgp_hodlr_t* h, double* buf_dev, int64_t rows_pad) {
+  if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
+  const int64_t cols = top_cols(h);
+  if (cols == 0 || h->nloc == 0) return BGP_OK;
+  if (rows_pad < h->nloc) { set_error("rows_pad too small"); return BGP_ERR_INVALID; }
+  pack_rows_kernel<<<1184, 256, 0, h->sA>>>(h->d_U.p, h->n, h->row0, h->nloc, cols, buf_dev, rows_pad);
+  BGP_LAUNCH_CHECK();
+  BGP_CUDA(cudaStreamSynchronize(h->sA));
+  return BGP_OK;
+}
+
+int bgp_hodlr_import_top(bgp_hodlr_t* h, const double* all_buf_dev, int64_t rows_pad) {
+  if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
+  const int64_t cols = top_cols(h);
+  if (cols == 0) return BGP_OK;
+  for (size_t s = 0; s < h->shard_rows.size(); ++s) {
+    if ((int)s == h->opts.shard_rank) continue;  // own rows are already in place
+    unpack_rows_kernel<<<1184, 256, 0, h->sA>>>(h->d_U.p, h->n, h->shard_row0[s], h->shard_rows[s], cols,
+                                                all_buf_dev + (int64_t)s * cols * rows_pad, rows_pad);
+    BGP_LAUNCH_CHECK();
+  }
+  BGP_CUDA(cudaStreamSynchronize(h->sA));
+  return BGP_OK;
+}
+
+int bgp_hodlr_finish_top(bgp_hodlr_t* h) {
+  if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
+  cudaStream_t s = h->sA;
+  const int nlev = (int)h->levels.size();
+  const int cut = std::min(h->cut_depth, nlev);
+  for (int l = cut - 1; l >= 0; --l) {
+    const LevelInfo& L = h->levels[l];
+    BGP_TRY(launch_level(h, L, h->d_U.p, h->n, L.ucol + L.r, L.ucol, 1, 0, L.ucol, s));
+  }
+  // local log-det: owned leaves + owned nodes; top nodes counted once (by shard 0)
+  const int nl = (int)h->leaves.size();
+  int ndesc = 0;
+  for (auto& L : h->levels) ndesc += (int)L.nodes.size();
+  std::vector<double> ld_leaf(nl), ld_node(ndesc);
+  if (nl) BGP_CUDA(cudaMemcpyAsync(ld_leaf.data(), h->d_leaf_logdet.p, sizeof(double) * nl, cudaMemcpyDeviceToHost, s));
+  if (ndesc) BGP_CUDA(cudaMemcpyAsync(ld_node.data(), h->d_node_logdet.p, sizeof(double) * ndesc, cudaMemcpyDeviceToHost, s));
+  BGP_CUDA(cudaStreamSynchronize(s));
+  double ld = 0.0;
+  for (double v : ld_leaf) ld += v;
+  for (int l = 0; l < nlev; ++l) {
+    const LevelInfo& L = h->levels[l];
+    if (l < cut && h->opts.shard_rank != 0) continue;
+    for (size_t i = 0; i < L.nodes.size(); ++i) ld += ld_node[L.desc_off + i];
+  }
+  h->log_det = ld;  // PARTIAL: the host sums over shards
+  h->computed = true;
+  return BGP_OK;
+}
+
+int bgp_hodlr_solve_local_dev(bgp_hodlr_t* h, double* b_dev, int64_t nrhs, int64_t ldb) {
+  if (!h || !h->computed) { set_error("the solver has not been computed"); return BGP_ERR_NOT_COMPUTED; }
+  BGP_TRY(hodlr_solve_dev(h, b_dev, nrhs, ldb, h->sA, 1));
+  BGP_CUDA(cudaStreamSynchronize(h->sA));
+  return BGP_OK;
+}
+int bgp_hodlr_solve_top_dev(bgp_hodlr_t* h, double* b_dev, int64_t nrhs, int64_t ldb) {
+  if (!h || !h->computed) { set_error("the solver has not been computed"); return BGP_ERR_NOT_COMPUTED; }
+  BGP_TRY(hodlr_solve_dev(h, b_dev, nrhs, ldb, h->sA, 2));
+  BGP_CUDA(cudaStreamSynchronize(h->sA));
+  return BGP_OK;
+}
+
+}  // extern "C"

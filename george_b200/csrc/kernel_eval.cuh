@@ -1,0 +1,295 @@
+// kernel_eval.cuh — device-side covariance evaluation from the POD kernel program.
+//
+// The reference evaluates k(x1, x2) through a heap tree of virtual C++ objects
+// (src/george/include/george/kernels.h:21-40, Sum :75-109, Product :111-163, per-kernel classes below that; metrics in
+// metrics.h:71-253).  Here the tree is a postfix program that a thread interprets with a small register stack;
+// re-parametrisations (exp(-log M), pi * exp(-log P), ...) are done ONCE on the host with the same libm calls the
+// reference makes (update_reparams(), Metric::set_parameter metrics.h:46-49), so the device only sees the digested
+// constants and differs from the CPU path by the <=2 ulp of CUDA's exp/sin/cos/pow.
+#pragma once
+
+#include "common.cuh"
+
+namespace bgp {
+
+#define BGP_MAX_LEAVES 16
+#define BGP_STACK 8  // operand-stack depth of the interpreter (validated on the host)
+
+struct DevLeaf {
+  int kernel_type, metric_type, naxes, blocked, n_params, n_metric, param_off, _pad;
+  int axes[BGP_MAX_DIM];
+  double p[4];                  // raw parameters
+  double rp[2];                 // re-parametrised constants
+  double mvec[BGP_MAX_METRIC];  // metric vector_ (metrics.h:46-49,170-180)
+  double mn[BGP_MAX_DIM], mx[BGP_MAX_DIM];
+};
+
+struct DevProgram {
+  int n_nodes, ndim, n_params_total, n_leaves;
+  int flags;  // bit0: every leaf is a stationary isotropic/axis-aligned or 1-axis kernel (fast path hint)
+  int _pad[3];
+  signed char code[BGP_MAX_NODES];  // >=0: leaf index, -1: sum, -2: product
+  DevLeaf leaf[BGP_MAX_LEAVES];
+};
+
+// number of bytes of a program that are live (header + used leaves): what kernels stage into shared memory
+__host__ __device__ inline size_t program_bytes(int n_leaves) {
+  return offsetof(DevProgram, leaf) + sizeof(DevLeaf) * (size_t)n_leaves;
+}
+
+// host: digest + validate a bgp_kernel_spec_t (replaces parser.h:14-509 + update_reparams())
+int build_dev_program(const bgp_kernel_spec_t* spec, DevProgram* out);
+
+#ifdef __CUDACC__
+
+// cooperative copy of the live part of the program into shared memory (all threads of the CTA must call)
+__device__ __forceinline__ void stage_program(DevProgram* dst_smem, const DevProgram* __restrict__ src) {
+  const int nl = src->n_leaves;
+  const int words = (int)(program_bytes(nl) / 4);
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst_smem);
+  for (int i = threadIdx.x; i < words; i += blockDim.x) d[i] = s[i];
+}
+
+__device__ __forceinline__ bool general_is_diag(int i) {
+  for (int j = 0, d = 2; j <= i; j += d, ++d)
+    if (i == j) return true;
+  return false;
+}
+
+// r2 = (x1-x2)^T M^-1 (x1-x2) on the leaf's axes.  metrics.h:76-85 | 108-117 | 182-197
+__device__ __forceinline__ double metric_r2(const DevLeaf& L, const double* x1, const double* x2) {
+  double r2 = 0.0;
+  if (L.metric_type == BGP_METRIC_ISOTROPIC) {
+    for (int i = 0; i < L.naxes; ++i) {
+      const double d = x1[L.axes[i]] - x2[L.axes[i]];
+      r2 += d * d;
+    }
+    return r2 * L.mvec[0];
+  }
+  if (L.metric_type == BGP_METRIC_AXIS_ALIGNED) {
+    for (int i = 0; i < L.naxes; ++i) {
+      const double d = x1[L.axes[i]] - x2[L.axes[i]];
+      r2 += d * d * L.mvec[i];
+    }
+    return r2;
+  }
+  // general: forward substitution with the packed inverse-diagonal Cholesky factor (metrics.h:144-151)
+  double r[BGP_MAX_DIM];
+  const int n = L.naxes;
+  int k = 0;
+  for (int i = 0; i < n; ++i) {
+    double b = x1[L.axes[i]] - x2[L.axes[i]];
+    for (int j = 0; j < i; ++j, ++k) b -= L.mvec[k] * r[j];
+    b *= L.mvec[k++];
+    r[i] = b;
+    r2 += b * b;
+  }
+  return r2;
+}
+
+// metric value + gradient wrt the metric parameters.  metrics.h:87-91 | 119-131 | 201-231
+__device__ inline double metric_r2_grad(const DevLeaf& L, const double* x1, const double* x2, double* grad) {
+  double r2 = 0.0;
+  if (L.metric_type == BGP_METRIC_ISOTROPIC) {
+    r2 = metric_r2(L, x1, x2);
+    grad[0] = -r2;
+    return r2;
+  }
+  if (L.metric_type == BGP_METRIC_AXIS_ALIGNED) {
+    for (int i = 0; i < L.naxes; ++i) {
+      double d = x1[L.axes[i]] - x2[L.axes[i]];
+      d = d * d * L.mvec[i];
+      r2 += d;
+      grad[i] = -d;
+    }
+    return r2;
+  }
+  double r[BGP_MAX_DIM], Lir[BGP_MAX_DIM];
+  const int n = L.naxes;
+  int k = 0;
+  for (int i = 0; i < n; ++i) {
+    double b = x1[L.axes[i]] - x2[L.axes[i]];
+    for (int j = 0; j < i; ++j, ++k) b -= L.mvec[k] * r[j];
+    b *= L.mvec[k++];
+    r[i] = b;
+    Lir[i] = b;
+    r2 += b * b;
+  }
+  // backward substitution (metrics.h:153-164)
+  const int k0 = (n + 1) * n / 2;
+  for (int i = n - 1; i >= 0; --i) {
+    int kk = k0 - n + i;
+    for (int j = n - 1; j > i; --j) {
+      r[i] -= L.mvec[kk] * r[j];
+      kk -= j;
+    }
+    r[i] *= L.mvec[kk];
+  }
+  k = 0;
+  for (int i = 0; i < n; ++i) {
+    grad[k] = -2 * r[i] * Lir[i] * exp(L.mvec[k]);  // metrics.h:222 (sic: exp of the stored inverse-diagonal entry)
+    k++;
+    for (int j = i + 1; j < n; ++j) grad[k++] = -2 * r[j] * Lir[i];
+  }
+  return r2;
+}
+
+__device__ __forceinline__ bool out_of_block(const DevLeaf& L, const double* x1, const double* x2) {
+  for (int i = 0; i < L.naxes; ++i) {
+    const int j = L.axes[i];
+    if (x1[j] < L.mn[i] || x1[j] > L.mx[i] || x2[j] < L.mn[i] || x2[j] > L.mx[i]) return true;
+  }
+  return false;
+}
+
+// radial profiles k(r2): kernels.h:1890-1894 ExpSquared | 2084-2090 Matern32 | 1319-1325 Matern52 | 651-655 Exp |
+// 418-425 RationalQuadratic
+__device__ __forceinline__ double radial_value(const DevLeaf& L, double r2) {
+  switch (L.kernel_type) {
+    case BGP_K_EXP_SQUARED: return exp(-0.5 * r2);
+    case BGP_K_MATERN32: { const double r = sqrt(3.0 * r2); return (1.0 + r) * exp(-r); }
+    case BGP_K_MATERN52: { const double r = sqrt(5.0 * r2); return (1 + r + 5.0 * r2 / 3.0) * exp(-r); }
+    case BGP_K_EXP: return exp(-sqrt(r2));
+    case BGP_K_RATIONAL_QUADRATIC: return pow(1 + 0.5 * r2 / L.rp[0], -L.rp[0]);
+  }
+  return 0.0;
+}
+// dk/dr2: kernels.h:1912-1916 | 2108-2114 | 1343-1349 | Exp.yml | 454-461
+__device__ __forceinline__ double radial_gradient(const DevLeaf& L, double r2) {
+  switch (L.kernel_type) {
+    case BGP_K_EXP_SQUARED: return -0.5 * exp(-0.5 * r2);
+    case BGP_K_MATERN32: { const double r = sqrt(3.0 * r2); return -3.0 * 0.5 * exp(-r); }
+    case BGP_K_MATERN52: { const double r = sqrt(5.0 * r2); return -5 * (1 + r) * exp(-r) / 6.0; }
+    case BGP_K_EXP: { if (r2 < 2.220446049250313e-16) return 0.0; const double r = sqrt(r2); return -0.5 * exp(-r) / r; }
+    case BGP_K_RATIONAL_QUADRATIC: return -0.5 * pow(1 + 0.5 * r2 / L.rp[0], -L.rp[0] - 1);
+  }
+  return 0.0;
+}
+
+// per-axis value of the non-stationary kernels (summed over the leaf's axes, e.g. kernels.h:1720-1732)
+__device__ __forceinline__ double axis_value(const DevLeaf& L, double x1, double x2) {
+  switch (L.kernel_type) {
+    case BGP_K_LINEAR: if (L.p[1] == 0.0) return L.rp[0]; return pow(x1 * x2, L.p[1]) * L.rp[0];
+    case BGP_K_LOCAL_GAUSSIAN: { const double d1 = x1 - L.p[0], d2 = x2 - L.p[0]; return exp(-(d1 * d1 + d2 * d2) * L.rp[0]); }
+    case BGP_K_EMPTY: return 0.0;
+    case BGP_K_COSINE: return cos((x1 - x2) * L.rp[0]);
+    case BGP_K_EXP_SINE2: { const double s = sin((x1 - x2) * L.rp[0]); return exp(-L.p[0] * s * s); }
+    case BGP_K_CONSTANT: return L.rp[0];
+    case BGP_K_POLYNOMIAL: if (L.p[1] == 0.0) return 1.0; return pow(x1 * x2 + L.rp[0], L.p[1]);
+    case BGP_K_DOT_PRODUCT: return x1 * x2;
+  }
+  return 0.0;
+}
+__device__ inline double axis_param_gradient(const DevLeaf& L, int q, double x1, double x2) {
+  switch (L.kernel_type) {
+    case BGP_K_LINEAR: if (L.p[1] == 0.0) return -L.rp[0]; return -pow(x1 * x2, L.p[1]) * L.rp[0];
+    case BGP_K_LOCAL_GAUSSIAN: {
+      const double d1 = x1 - L.p[0], d2 = x2 - L.p[0];
+      if (q == 0) return 2 * exp(-(d1 * d1 + d2 * d2) * L.rp[0]) * L.rp[0] * (d1 + d2);
+      const double arg = (d1 * d1 + d2 * d2) * L.rp[0];
+      return exp(-arg) * arg;
+    }
+    case BGP_K_COSINE: { const double r = L.rp[0] * (x1 - x2); return r * sin(r); }
+    case BGP_K_EXP_SINE2: {
+      if (q == 0) { const double s = sin((x1 - x2) * L.rp[0]), s2 = s * s; return -s2 * exp(-L.p[0] * s2); }
+      const double arg = (x1 - x2) * L.rp[0], s = sin(arg), c = cos(arg), A = exp(-L.p[0] * s * s);
+      return 2 * L.p[0] * arg * c * s * A;
+    }
+    case BGP_K_CONSTANT: return L.rp[0];
+    case BGP_K_POLYNOMIAL: if (L.p[1] == 0.0) return 0.0; return L.rp[0] * pow(x1 * x2 + L.rp[0], L.p[1] - 1.0) * L.p[1];
+  }
+  return 0.0;
+}
+
+__device__ __forceinline__ double leaf_value(const DevLeaf& L, const double* x1, const double* x2) {
+  if (L.metric_type != BGP_METRIC_NONE) {
+    if (L.blocked && out_of_block(L, x1, x2)) return 0.0;
+    return radial_value(L, metric_r2(L, x1, x2));
+  }
+  double v = 0.0;
+  for (int i = 0; i < L.naxes; ++i) v += axis_value(L, x1[L.axes[i]], x2[L.axes[i]]);
+  return v;
+}
+
+// k(x1, x2): postfix interpreter with a shift-register operand stack (no dynamically indexed local memory).
+// P lives in shared memory; x1/x2 point at `ndim` doubles (shared, global or local).
+__device__ __forceinline__ double kernel_value(const DevProgram& P, const double* x1, const double* x2) {
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0;
+  const int n = P.n_nodes;
+  for (int i = 0; i < n; ++i) {
+    const int c = P.code[i];
+    if (c >= 0) {
+      const double v = leaf_value(P.leaf[c], x1, x2);
+      s7 = s6; s6 = s5; s5 = s4; s4 = s3; s3 = s2; s2 = s1; s1 = s0; s0 = v;
+    } else {
+      s0 = (c == -1) ? (s1 + s0) : (s1 * s0);  // kernels.h:78-80 | 114-116
+      s1 = s2; s2 = s3; s3 = s4; s4 = s5; s5 = s6; s6 = s7;
+    }
+  }
+  return s0;
+}
+
+// value + hyper-parameter gradient (kernels.h:81-94 Sum, 117-139 Product, per-leaf gradient() methods).
+// grad has n_params_total entries; entries with which[i]==0 are 0.  Not on the log-likelihood hot path.
+__device__ inline double kernel_value_grad(const DevProgram& P, const double* x1, const double* x2,
+                                           const unsigned* which, double* grad) {
+  double val[BGP_STACK];
+  int lo[BGP_STACK], hi[BGP_STACK];
+  int sp = 0;
+  for (int i = 0; i < P.n_nodes; ++i) {
+    const int c = P.code[i];
+    if (c >= 0) {
+      const DevLeaf& L = P.leaf[c];
+      const int np = L.n_params + L.n_metric, off = L.param_off;
+      for (int q = 0; q < np; ++q) grad[off + q] = 0.0;
+      double v;
+      if (L.metric_type != BGP_METRIC_NONE) {
+        if (L.blocked && out_of_block(L, x1, x2)) {
+          v = 0.0;
+        } else {
+          bool any = false;
+          for (int q = L.n_params; q < np; ++q) any |= (which[off + q] != 0);
+          double r2;
+          if (any) {
+            double mg[BGP_MAX_METRIC];
+            r2 = metric_r2_grad(L, x1, x2, mg);
+            const double rg = radial_gradient(L, r2);
+            for (int q = 0; q < L.n_metric; ++q) grad[off + L.n_params + q] = mg[q] * rg;
+          } else {
+            r2 = metric_r2(L, x1, x2);
+          }
+          if (L.kernel_type == BGP_K_RATIONAL_QUADRATIC && which[off]) {  // kernels.h:446-452
+            const double a = L.rp[0], t1 = 1.0 + 0.5 * r2 / a, t2 = 2.0 * a * t1;
+            grad[off] = a * pow(t1, -a) * (r2 / t2 - log(t1));
+          }
+          v = radial_value(L, r2);
+        }
+      } else {
+        v = 0.0;
+        for (int a = 0; a < L.naxes; ++a) v += axis_value(L, x1[L.axes[a]], x2[L.axes[a]]);
+        for (int q = 0; q < L.n_params; ++q) {
+          if (!which[off + q]) continue;
+          double g = 0.0;
+          for (int a = 0; a < L.naxes; ++a) g += axis_param_gradient(L, q, x1[L.axes[a]], x2[L.axes[a]]);
+          grad[off + q] = g;
+        }
+      }
+      val[sp] = v; lo[sp] = off; hi[sp] = off + np; sp++;
+    } else if (c == -1) {
+      sp--; val[sp - 1] += val[sp]; hi[sp - 1] = hi[sp];
+    } else {
+      sp--;
+      const double k1 = val[sp - 1], k2 = val[sp];
+      for (int q = lo[sp - 1]; q < hi[sp - 1]; ++q) grad[q] *= k2;
+      for (int q = lo[sp]; q < hi[sp]; ++q) grad[q] *= k1;
+      val[sp - 1] = k1 * k2; hi[sp - 1] = hi[sp];
+    }
+  }
+  for (int q = 0; q < P.n_params_total; ++q) if (!which[q]) grad[q] = 0.0;
+  return val[0];
+}
+
+#endif  // __CUDACC__
+
+}  // namespace bgp

@@ -1,0 +1,339 @@
+// kmat.cu — K1/K2: fused pairwise-metric + covariance kernel-matrix build (value and hyper-parameter gradient).
+//
+// Replaces the serial double loops of KernelInterface::value_symmetric / value_general / value_diagonal /
+// gradient_symmetric / gradient_general (reference src/george/kernel_interface.cpp:47-125).
+//
+// Roofline: HBM-write bound, 8 algorithmic bytes per entry (x reads are n*ndim*8 B, negligible).  Coordinates of a tile
+// are staged into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier; falls back to plain loads for
+// unaligned tails); every thread owns two adjacent output columns so a warp writes 512 contiguous bytes per row
+// (st.global.v2.f64).  The symmetric build evaluates only tiles on/above the diagonal and writes the mirrored tile
+// through a shared-memory transpose so both stores stay coalesced.
+#include <algorithm>
+#include "common.cuh"
+#include "kernel_eval.cuh"
+
+namespace bgp {
+
+constexpr int KM_TI = 64;    // tile rows
+constexpr int KM_TJ = 128;   // tile cols (general build)
+constexpr int KM_THREADS = 256;
+
+// cooperative tile load of `count` doubles; TMA bulk when 16-byte aligned & sized, plain loads otherwise.
+// `bar` is a CTA-shared mbarrier already initialised with count 1; `*phase` flips on every TMA use.
+__device__ __forceinline__ void load_coords(double* dst, const double* __restrict__ src, int count, uint64_t* bar,
+                                            uint32_t& phase) {
+  const uint32_t bytes = (uint32_t)count * 8u;
+  const bool bulk = ((bytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && bytes > 0;
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, bytes);
+      tma_load_1d(dst, src, bytes, bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+  } else {
+    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+  }
+}
+
+struct KmatSmem {
+  DevProgram prog;
+  uint64_t bar;
+};
+
+// out[i*ld + j] = k(x1_i, x2_j)
+__global__ void __launch_bounds__(KM_THREADS) kmat_general_kernel(const DevProgram* __restrict__ gprog,
+                                                                  const double* __restrict__ x1, int64_t n1,
+                                                                  const double* __restrict__ x2, int64_t n2,
+                                                                  double* __restrict__ out, int64_t ld) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KmatSmem* S = reinterpret_cast<KmatSmem*>(smem_raw);
+  const int nd = gprog->ndim;
+  double* sx1 = reinterpret_cast<double*>(smem_raw + ((sizeof(KmatSmem) + 15) & ~size_t(15)));
+  double* sx2 = sx1 + KM_TI * nd + ((KM_TI * nd) & 1);
+
+  stage_program(&S->prog, gprog);
+  if (threadIdx.x == 0) { mbar_init(&S->bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  uint32_t phase = 0;
+
+  const int64_t i0 = (int64_t)blockIdx.y * KM_TI, j0 = (int64_t)blockIdx.x * KM_TJ;
+  const int ni = (int)min((int64_t)KM_TI, n1 - i0), nj = (int)min((int64_t)KM_TJ, n2 - j0);
+  load_coords(sx1, x1 + i0 * nd, ni * nd, &S->bar, phase);
+  load_coords(sx2, x2 + j0 * nd, nj * nd, &S->bar, phase);
+  __syncthreads();
+
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int ja = 2 * tx, jb = 2 * tx + 1;
+  const bool vec = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && ((j0 & 1) == 0);
+  if (ja < nj) {
+    const double* xa = sx2 + ja * nd;
+    const double* xb = sx2 + (jb < nj ? jb : ja) * nd;
+    for (int i = ty; i < ni; i += KM_THREADS / 64) {
+      const double* xi = sx1 + i * nd;
+      const double va = kernel_value(S->prog, xi, xa);
+      const double vb = (jb < nj) ? kernel_value(S->prog, xi, xb) : 0.0;
+      double* o = out + (i0 + i) * ld + j0 + ja;
+      if (vec && jb < nj) {
+        *reinterpret_cast<double2*>(o) = make_double2(va, vb);
+      } else {
+        o[0] = va;
+        if (jb < nj) o[1] = vb;
+      }
+    }
+  }
+}
+
+// symmetric build: out (n x n, leading dimension ld), optional diag_add on the diagonal (basic.py:64-65 fused)
+constexpr int KS_T = 64;
+__global__ void __launch_bounds__(KM_THREADS) kmat_symmetric_kernel(const DevProgram* __restrict__ gprog,
+                                                                    const double* __restrict__ x, int64_t n,
+                                                                    const double* __restrict__ diag_add,
+                                                                    double* __restrict__ out, int64_t ld) {
+  if (blockIdx.x < blockIdx.y) return;  // tiles below the diagonal are produced by the mirror store
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KmatSmem* S = reinterpret_cast<KmatSmem*>(smem_raw);
+  const int nd = gprog->ndim;
+  double* sxi = reinterpret_cast<double*>(smem_raw + ((sizeof(KmatSmem) + 15) & ~size_t(15)));
+  double* sxj = sxi + KS_T * nd + ((KS_T * nd) & 1);
+  double* tile = sxj + KS_T * nd + ((KS_T * nd) & 1);  // KS_T x (KS_T+1)
+
+  stage_program(&S->prog, gprog);
+  if (threadIdx.x == 0) { mbar_init(&S->bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  uint32_t phase = 0;
+
+  const int64_t i0 = (int64_t)blockIdx.y * KS_T, j0 = (int64_t)blockIdx.x * KS_T;
+  const int ni = (int)min((int64_t)KS_T, n - i0), nj = (int)min((int64_t)KS_T, n - j0);
+  const bool on_diag = (blockIdx.x == blockIdx.y);
+  load_coords(sxi, x + i0 * nd, ni * nd, &S->bar, phase);
+  load_coords(sxj, x + j0 * nd, nj * nd, &S->bar, phase);
+  __syncthreads();
+
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // one column per thread, 16 rows
+  if (on_diag) {
+    // evaluate k(x_i, x_j) for j >= i only and mirror, exactly like the reference loop (kernel_interface.cpp:69-75):
+    // FMA contraction makes k(a, b) and k(b, a) differ in the last bit for some kernels.
+    if (tx < nj) {
+      const double* xj = sxj + tx * nd;
+      for (int i = ty; i < ni && i <= tx; i += KM_THREADS / 64) {
+        double v = kernel_value(S->prog, sxi + i * nd, xj);
+        if (i == tx && diag_add) v += diag_add[i0 + i];
+        tile[i * (KS_T + 1) + tx] = v;
+      }
+    }
+    __syncthreads();
+    if (tx < nj) {
+      for (int i = ty; i < ni; i += KM_THREADS / 64)
+        out[(i0 + i) * ld + j0 + tx] = (i <= tx) ? tile[i * (KS_T + 1) + tx] : tile[tx * (KS_T + 1) + i];
+    }
+    return;
+  }
+  if (tx < nj) {
+    const double* xj = sxj + tx * nd;
+    for (int i = ty; i < ni; i += KM_THREADS / 64) {
+      const double v = kernel_value(S->prog, sxi + i * nd, xj);
+      out[(i0 + i) * ld + j0 + tx] = v;
+      tile[i * (KS_T + 1) + tx] = v;
+    }
+  }
+  __syncthreads();
+  // mirrored tile: out[j0 + c][i0 + r] = tile[r][c], r fastest across threads for coalescing
+  if (tx < ni) {
+    for (int c = ty; c < nj; c += KM_THREADS / 64) out[(j0 + c) * ld + i0 + tx] = tile[tx * (KS_T + 1) + c];
+  }
+}
+
+__global__ void kmat_diagonal_kernel(const DevProgram* __restrict__ gprog, const double* __restrict__ x1,
+                                     const double* __restrict__ x2, int64_t n, double* __restrict__ out) {
+  __shared__ DevProgram P;
+  stage_program(&P, gprog);
+  __syncthreads();
+  const int nd = P.ndim;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = kernel_value(P, x1 + i * nd, x2 + i * nd);
+}
+
+// gradient: out[(i*n2 + j)*np + q].  One thread per pair; not on the log-likelihood path.
+__global__ void __launch_bounds__(128) kmat_gradient_kernel(const DevProgram* __restrict__ gprog,
+                                                            const unsigned* __restrict__ which,
+                                                            const double* __restrict__ x1, int64_t n1,
+                                                            const double* __restrict__ x2, int64_t n2,
+                                                            double* __restrict__ out, int symmetric) {
+  __shared__ DevProgram P;
+  __shared__ unsigned sw[BGP_MAX_LEAVES * (4 + BGP_MAX_METRIC)];
+  stage_program(&P, gprog);
+  __syncthreads();
+  const int np = P.n_params_total, nd = P.ndim;
+  for (int q = threadIdx.x; q < np; q += blockDim.x) sw[q] = which[q];
+  __syncthreads();
+  const int64_t total = n1 * n2;
+  double g[64];
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / n2, j = t - i * n2;
+    // the reference evaluates (i, j) with i <= j and mirrors (kernel_interface.cpp:116-121)
+    const double* a = x1 + ((symmetric && j < i) ? j : i) * nd;
+    const double* b = x2 + ((symmetric && j < i) ? i : j) * nd;
+    kernel_value_grad(P, a, b, sw, g);
+    double* o = out + t * np;
+    for (int q = 0; q < np; ++q) o[q] = g[q];
+  }
+}
+
+static size_t kmat_smem_general(int nd) {
+  return ((sizeof(KmatSmem) + 15) & ~size_t(15)) + sizeof(double) * ((size_t)KM_TI * nd + 1 + (size_t)KM_TJ * nd + 1);
+}
+static size_t kmat_smem_sym(int nd) {
+  return ((sizeof(KmatSmem) + 15) & ~size_t(15)) +
+         sizeof(double) * (2 * ((size_t)KS_T * nd + 1) + (size_t)KS_T * (KS_T + 1));
+}
+
+// ---- device-pointer launchers (used by the solvers) -------------------------------------------------------------
+int kmat_general_launch(const DevProgram* dprog, int nd, const double* x1, int64_t n1, const double* x2, int64_t n2,
+                        double* out, int64_t ld, cudaStream_t s) {
+  if (n1 == 0 || n2 == 0) return BGP_OK;
+  const size_t smem = kmat_smem_general(nd);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(kmat_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+  dim3 grid((unsigned)((n2 + KM_TJ - 1) / KM_TJ), (unsigned)((n1 + KM_TI - 1) / KM_TI));
+  if (grid.y > 65535) { set_error("kmat_general: n1 too large for one launch"); return BGP_ERR_INVALID; }
+  kmat_general_kernel<<<grid, KM_THREADS, smem, s>>>(dprog, x1, n1, x2, n2, out, ld);
+  BGP_LAUNCH_CHECK();
+  return BGP_OK;
+}
+
+int kmat_symmetric_launch(const DevProgram* dprog, int nd, const double* x, int64_t n, const double* diag_add,
+                          double* out, int64_t ld, cudaStream_t s) {
+  if (n == 0) return BGP_OK;
+  const size_t smem = kmat_smem_sym(nd);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(kmat_symmetric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+  const unsigned nt = (unsigned)((n + KS_T - 1) / KS_T);
+  if (nt > 65535) { set_error("kmat_symmetric: n too large for one launch"); return BGP_ERR_INVALID; }
+  dim3 grid(nt, nt);
+  kmat_symmetric_kernel<<<grid, KM_THREADS, smem, s>>>(dprog, x, n, diag_add, out, ld);
+  BGP_LAUNCH_CHECK();
+  return BGP_OK;
+}
+
+// upload a digested program to a fresh device buffer
+int upload_program(const DevProgram& P, DevBuf<DevProgram>& buf, cudaStream_t s) {
+  BGP_TRY(buf.reserve(1, s));
+  BGP_CUDA(cudaMemcpyAsync(buf.p, &P, sizeof(DevProgram), cudaMemcpyHostToDevice, s));
+  return BGP_OK;
+}
+
+}  // namespace bgp
+
+using namespace bgp;
+
+// ---- host-pointer entry points --------------------------------------------------------------------------------
+static int kmat_host(const bgp_kernel_spec_t* spec, const double* x1, int64_t n1, const double* x2, int64_t n2,
+                     double* out, int mode /*0 general,1 symmetric,2 diagonal*/) {
+  BGP_TRY(require_device());
+  DevProgram P;
+  BGP_TRY(build_dev_program(spec, &P));
+  if (n1 < 0 || n2 < 0) { set_error("negative size"); return BGP_ERR_INVALID; }
+  cudaStream_t s = 0;
+  const int nd = P.ndim;
+  DevBuf<DevProgram> dprog;
+  DevBuf<double> dx1, dx2, dout;
+  BGP_TRY(upload_program(P, dprog, s));
+  BGP_TRY(dx1.alloc((size_t)n1 * nd, s));
+  if (n1) BGP_CUDA(cudaMemcpyAsync(dx1.p, x1, sizeof(double) * n1 * nd, cudaMemcpyHostToDevice, s));
+  const double* px2 = dx1.p;
+  if (mode != 1) {
+    BGP_TRY(dx2.alloc((size_t)n2 * nd, s));
+    if (n2) BGP_CUDA(cudaMemcpyAsync(dx2.p, x2, sizeof(double) * n2 * nd, cudaMemcpyHostToDevice, s));
+    px2 = dx2.p;
+  }
+  const size_t nout = mode == 2 ? (size_t)n1 : (size_t)n1 * (size_t)(mode == 1 ? n1 : n2);
+  BGP_TRY(dout.alloc(nout, s));
+  if (nout == 0) return BGP_OK;
+  if (mode == 0) BGP_TRY(kmat_general_launch(dprog.p, nd, dx1.p, n1, px2, n2, dout.p, n2, s));
+  else if (mode == 1) BGP_TRY(kmat_symmetric_launch(dprog.p, nd, dx1.p, n1, nullptr, dout.p, n1, s));
+  else {
+    const int blocks = (int)std::min<int64_t>((n1 + 255) / 256, 4 * num_sms());
+    kmat_diagonal_kernel<<<blocks, 256, 0, s>>>(dprog.p, dx1.p, px2, n1, dout.p);
+    BGP_LAUNCH_CHECK();
+  }
+  BGP_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, s));
+  BGP_CUDA(cudaStreamSynchronize(s));
+  return BGP_OK;
+}
+
+static int kmat_grad_host(const bgp_kernel_spec_t* spec, const uint32_t* which, const double* x1, int64_t n1,
+                          const double* x2, int64_t n2, double* out, int symmetric) {
+  BGP_TRY(require_device());
+  DevProgram P;
+  BGP_TRY(build_dev_program(spec, &P));
+  const int np = P.n_params_total, nd = P.ndim;
+  if (np > 64) { set_error("gradient supports at most 64 hyper-parameters"); return BGP_ERR_INVALID; }
+  if (np == 0 || n1 == 0 || n2 == 0) return BGP_OK;
+  cudaStream_t s = 0;
+  DevBuf<DevProgram> dprog;
+  DevBuf<double> dx1, dx2, dout;
+  DevBuf<unsigned> dw;
+  BGP_TRY(upload_program(P, dprog, s));
+  BGP_TRY(dx1.alloc((size_t)n1 * nd, s));
+  BGP_CUDA(cudaMemcpyAsync(dx1.p, x1, sizeof(double) * n1 * nd, cudaMemcpyHostToDevice, s));
+  const double* px2 = dx1.p;
+  if (!symmetric) {
+    BGP_TRY(dx2.alloc((size_t)n2 * nd, s));
+    BGP_CUDA(cudaMemcpyAsync(dx2.p, x2, sizeof(double) * n2 * nd, cudaMemcpyHostToDevice, s));
+    px2 = dx2.p;
+  }
+  BGP_TRY(dw.alloc(np, s));
+  BGP_CUDA(cudaMemcpyAsync(dw.p, which, sizeof(unsigned) * np, cudaMemcpyHostToDevice, s));
+  const size_t nout = (size_t)n1 * n2 * np;
+  BGP_TRY(dout.alloc(nout, s));
+  const int blocks = (int)std::min<int64_t>((n1 * n2 + 127) / 128, 16 * num_sms());
+  kmat_gradient_kernel<<<blocks, 128, 0, s>>>(dprog.p, dw.p, dx1.p, n1, px2, n2, dout.p, symmetric);
+  BGP_LAUNCH_CHECK();
+  BGP_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, s));
+  BGP_CUDA(cudaStreamSynchronize(s));
+  return BGP_OK;
+}
+
+extern "C" {
+
+int bgp_kmat_symmetric(const bgp_kernel_spec_t* spec, const double* x, int64_t n, double* out) {
+  return kmat_host(spec, x, n, x, n, out, 1);
+}
+int bgp_kmat_general(const bgp_kernel_spec_t* spec, const double* x1, int64_t n1, const double* x2, int64_t n2,
+                     double* out) {
+  return kmat_host(spec, x1, n1, x2, n2, out, 0);
+}
+int bgp_kmat_diagonal(const bgp_kernel_spec_t* spec, const double* x1, const double* x2, int64_t n, double* out) {
+  return kmat_host(spec, x1, n, x2, n, out, 2);
+}
+int bgp_kmat_gradient_symmetric(const bgp_kernel_spec_t* spec, const uint32_t* which, const double* x, int64_t n,
+                                double* out) {
+  return kmat_grad_host(spec, which, x, n, x, n, out, 1);
+}
+int bgp_kmat_gradient_general(const bgp_kernel_spec_t* spec, const uint32_t* which, const double* x1, int64_t n1,
+                              const double* x2, int64_t n2, double* out) {
+  return kmat_grad_host(spec, which, x1, n1, x2, n2, out, 0);
+}
+
+int bgp_kmat_symmetric_dev(const bgp_kernel_spec_t* spec, const double* x_dev, int64_t n, const double* diag_add_dev,
+                           double* out_dev, int64_t ld) {
+  BGP_TRY(require_device());
+  DevProgram P;
+  BGP_TRY(build_dev_program(spec, &P));
+  DevBuf<DevProgram> dprog;
+  BGP_TRY(upload_program(P, dprog, 0));
+  return kmat_symmetric_launch(dprog.p, P.ndim, x_dev, n, diag_add_dev, out_dev, ld, 0);
+}
+int bgp_kmat_general_dev(const bgp_kernel_spec_t* spec, const double* x1_dev, int64_t n1, const double* x2_dev,
+                         int64_t n2, double* out_dev, int64_t ld) {
+  BGP_TRY(require_device());
+  DevProgram P;
+  BGP_TRY(build_dev_program(spec, &P));
+  DevBuf<DevProgram> dprog;
+  BGP_TRY(upload_program(P, dprog, 0));
+  return kmat_general_launch(dprog.p, P.ndim, x1_dev, n1, x2_dev, n2, out_dev, ld, 0);
+}
+
+}  // extern "C"

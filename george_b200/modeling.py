@@ -77,15 +77,17 @@ class Model(object):
 
     def compute_gradient(self, *args, **kwargs):
         """First-order forward differences; subclasses overload with something analytic."""
-        p = self.get_parameter_vector()
+        # over the FULL vector so that get_gradient's thaw mask lines up (the reference differentiates only the thawed
+        # entries and then masks again, modeling.py:121-137, which breaks as soon as a parameter is frozen)
+        p = self.get_parameter_vector(include_frozen=True)
         f0 = self.get_value(*args, **kwargs)
         g = np.empty([len(p)] + list(np.shape(f0)), dtype=np.float64)
         for i, pi in enumerate(p):
             p[i] = pi + _FD_STEP
-            self.set_parameter_vector(p)
+            self.set_parameter_vector(p, include_frozen=True)
             g[i] = (self.get_value(*args, **kwargs) - f0) / _FD_STEP
             p[i] = pi
-            self.set_parameter_vector(p)
+            self.set_parameter_vector(p, include_frozen=True)
         return g
 
     def get_gradient(self, *args, **kwargs):

@@ -1,0 +1,165 @@
+# -*- coding: utf-8 -*-
+"""
+Multi-GPU HODLR: one process per GPU, the tree sharded by top-level sub-tree.
+
+The reference has no distributed code; what shards is the algorithmic independence of HODLR sub-trees
+(``hodlr.h:58-61,78-79``): below depth ``log2(P)`` the ``P`` sub-trees of ``~N/P`` points never touch each other's rows
+(``hodlr.h:95-102,240-253``).  Each rank
+
+1. factors its own sub-tree (leaves, ACAs, up-sweep) and applies it to ITS rows of the ``log2(P)`` top-level factor
+   panels (whose ACAs every rank recomputes redundantly from the replicated coordinates — no communication);
+2. takes part in ONE all-gather of those locally-solved row slices (the only data-path collective; NCCL over NVLink
+   when launched with ``torchrun`` on GPUs);
+3. finishes the ``P - 1`` top nodes redundantly (Gram, 2r x 2r LU, log-det, update).
+
+``log|K|`` is an all-reduce of one double; a solve is: local sub-tree solve on the owned slice, one all-gather of the
+vector, top nodes redundantly.  ``torch.distributed`` is plumbing only; all arithmetic is in ``csrc/hodlr.cu``.
+
+The exchange helpers at the bottom are backend-agnostic (tested with gloo on CPU tensors in ``tests/test_parallel.py``).
+"""
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._spec import flatten
+
+__all__ = ["ShardedHODLRSolver", "shard_ranges", "allgather_padded"]
+
+
+def shard_ranges(n, shard_count, min_size):
+    """Row ranges ``[(start, size), ...]`` of the depth-``log2(shard_count)`` nodes of the reference tree
+    (``hodlr.h:48-61``: ``half = size // 2``; a node splits iff ``half >= min_size``), or ``None`` when the tree is
+    too shallow to be cut that many ways."""
+    if shard_count < 1 or shard_count & (shard_count - 1):
+        raise ValueError("shard_count must be a power of two")
+    level = [(0, int(n))]
+    cut = shard_count.bit_length() - 1
+    for _ in range(cut):
+        nxt = []
+        for start, size in level:
+            half = size // 2
+            if half < min_size:
+                return None
+            nxt.append((start, half))
+            nxt.append((start + half, size - half))
+        level = nxt
+    return level
+
+
+def allgather_padded(local, rows_pad, group=None):
+    """All-gather 2-D blocks ``local`` (cols x rows_i, last dim contiguous) whose row counts differ by at most a few:
+    every rank pads to ``rows_pad`` and the result has shape ``(world, cols, rows_pad)``."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    cols, rows = local.shape
+    send = local
+    if rows != rows_pad:
+        send = torch.zeros((cols, rows_pad), dtype=local.dtype, device=local.device)
+        send[:, :rows] = local
+    send = send.contiguous()
+    out = torch.empty((world, cols, rows_pad), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out.view(-1), send.view(-1), group=group)
+    return out
+
+
+class ShardedHODLRSolver(object):
+    """Solver plugin with the ``HODLRSolver`` surface whose ``compute``/``dot_solve`` are collective over a
+    ``torch.distributed`` process group (one rank per GPU).  ``x``, ``yerr`` and ``y`` are replicated on every rank."""
+
+    def __init__(self, kernel, min_size=100, tol=0.1, seed=42, rank_capacity=0, exhaust="dense", group=None):
+        self.kernel = kernel
+        self.min_size, self.tol, self.seed = min_size, tol, seed
+        self.rank_capacity, self.exhaust, self.group = rank_capacity, exhaust, group
+        self._computed = False
+        self._log_det = None
+        self.solver = None
+
+    @property
+    def computed(self):
+        return self._computed
+
+    @property
+    def log_determinant(self):
+        return self._log_det
+
+    def compute(self, x, yerr):
+        import torch
+        import torch.distributed as dist
+        from .solvers._hodlr import HODLRSolver as Native
+        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.ndim == 1:
+            x = x[:, None]
+        yerr = np.ascontiguousarray(yerr, dtype=np.float64)
+        self._n = x.shape[0]
+        self._ranges = shard_ranges(self._n, world, self.min_size)
+        if self._ranges is None:
+            raise ValueError("the HODLR tree (N={0}, min_size={1}) is too shallow to shard {2} ways".format(
+                self._n, self.min_size, world))
+        self.solver = Native()
+        self.solver.compute(self.kernel, x, yerr, self.min_size, self.tol, self.seed, rank_capacity=self.rank_capacity,
+                            shard_rank=rank, shard_count=world, exhaust=self.exhaust)
+        lib, h = self.solver._lib, self.solver._ptr
+        ptr, row0, rows, cols, ld = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(lib.bgp_hodlr_top_panel(h, C.byref(ptr), C.byref(row0), C.byref(rows), C.byref(cols), C.byref(ld)))
+        assert (row0.value, rows.value) == self._ranges[rank]
+        self._rows_pad = max(sz for _, sz in self._ranges)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if cols.value > 0 and world > 1:
+            send = torch.empty((cols.value, self._rows_pad), dtype=torch.float64, device=dev)
+            _lib.check(lib.bgp_hodlr_export_top(h, C.c_void_p(send.data_ptr()), self._rows_pad))
+            gathered = torch.empty((world, cols.value, self._rows_pad), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(gathered.view(-1), send.view(-1), group=self.group)
+            torch.cuda.synchronize()
+            _lib.check(lib.bgp_hodlr_import_top(h, C.c_void_p(gathered.data_ptr()), self._rows_pad))
+        _lib.check(lib.bgp_hodlr_finish_top(h))
+        part = torch.tensor([self.solver.log_determinant], dtype=torch.float64, device=dev)
+        dist.all_reduce(part, group=self.group)
+        self._log_det = float(part.item())
+        self._computed = True
+
+    def _solve_dev(self, b):
+        """b: torch float64 CUDA tensor (n,), replicated; solved in place on every rank."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        lib, h = self.solver._lib, self.solver._ptr
+        n = self._n
+        _lib.check(lib.bgp_hodlr_solve_local_dev(h, C.c_void_p(b.data_ptr()), 1, n))
+        if world > 1:
+            start, size = self._ranges[rank]
+            send = torch.zeros(self._rows_pad, dtype=torch.float64, device=b.device)
+            send[:size] = b[start:start + size]
+            out = torch.empty(world * self._rows_pad, dtype=torch.float64, device=b.device)
+            dist.all_gather_into_tensor(out, send, group=self.group)
+            for s, (st, sz) in enumerate(self._ranges):
+                b[st:st + sz] = out[s * self._rows_pad:s * self._rows_pad + sz]
+            torch.cuda.synchronize()
+        _lib.check(lib.bgp_hodlr_solve_top_dev(h, C.c_void_p(b.data_ptr()), 1, n))
+        return b
+
+    def apply_inverse(self, y, in_place=False):
+        import torch
+        y = np.asarray(y, dtype=np.float64)
+        out = y if in_place else np.array(y)
+        cols = out.reshape(self._n, -1)
+        for c in range(cols.shape[1]):
+            b = torch.from_numpy(np.ascontiguousarray(cols[:, c])).cuda()
+            cols[:, c] = self._solve_dev(b).cpu().numpy()
+        return out.reshape(self._n, -1) if y.ndim == 1 else out
+
+    def dot_solve(self, y):
+        import torch
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        yd = torch.from_numpy(y).cuda()
+        b = self._solve_dev(yd.clone())
+        return float(torch.dot(yd, b).item())
+
+    def apply_sqrt(self, r):
+        raise NotImplementedError("apply_sqrt is not implemented for the HODLRSolver")
+
+    def get_inverse(self):
+        return self.apply_inverse(np.eye(self._n), in_place=True)

@@ -151,6 +151,10 @@ int bgp_dense_dot_solve(bgp_dense_t* h, const double* y, double* out);
 int bgp_dense_apply_sqrt(bgp_dense_t* h, const double* r, int64_t nr, double* out);
 /* basic.py:116-121: out (n, n); symmetric so the order does not matter. */
 int bgp_dense_get_inverse(bgp_dense_t* h, double* out);
+/* Pickle support (the reference pickles its numpy factor, tests/test_pickle.py:21-36): copy the lower Cholesky
+ * factor out (n*n, column-major, strictly-upper part zeroed) and load it back into a fresh handle. */
+int bgp_dense_export_factor(bgp_dense_t* h, double* out);
+int bgp_dense_import_factor(bgp_dense_t* h, const double* factor, int64_t n, double log_det);
 /* timing of the last compute: [0]=kernel-matrix build ms, [1]=potrf ms (device events). */
 int bgp_dense_last_timing(const bgp_dense_t* h, double* ms2);
 
@@ -175,8 +179,14 @@ typedef struct bgp_hodlr_opts {
    * `shard_rank` of `shard_count` (a power of two; 1 = whole tree).                             */
   int32_t shard_rank;
   int32_t shard_count;
-  int32_t reserved;
+  /* What to do when the ACA runs out of candidate rows (every remaining row's residual is < 1e-14):
+   *   BGP_EXHAUST_DENSE   (0, default) return the dense factorisation, rank = min(rows, cols), as hodlr.h:161-176 does;
+   *   BGP_EXHAUST_LOWRANK (1) keep the low-rank factors found so far: at that point EVERY row has been tested, so the
+   *                        approximation is verified to 1e-14 per entry and differs from the dense answer by rounding.
+   * Kernels that are exactly low rank on sorted 1-D inputs (Matern-3/2, Cosine, ...) hit this on most small nodes. */
+  int32_t exhaust_mode;
 } bgp_hodlr_opts_t;
+enum { BGP_EXHAUST_DENSE = 0, BGP_EXHAUST_LOWRANK = 1 };
 
 void bgp_hodlr_default_opts(bgp_hodlr_opts_t* o);
 int bgp_hodlr_create(bgp_hodlr_t** out);
@@ -226,6 +236,12 @@ int bgp_hodlr_last_work(const bgp_hodlr_t* h, double* w6);
  *   bgp_hodlr_top_panel(h, &ptr_dev, &rows, &cols, &ld): device pointer to the (N x cols) column-major panel
  *   bgp_hodlr_finish_top(h): Gram/LU/log-det/update of the nodes above the shard cut.               */
 int bgp_hodlr_top_panel(bgp_hodlr_t* h, double** ptr_dev, int64_t* row0, int64_t* rows, int64_t* cols, int64_t* ld);
+/* pack this shard's rows of the top panel into a contiguous (cols x rows_pad) device buffer (column c at c*rows_pad),
+ * and scatter the all-gathered buffers (shard s at s*cols*rows_pad) of all shards back into the panel. */
+int bgp_hodlr_export_top(bgp_hodlr_t* h, double* buf_dev, int64_t rows_pad);
+int bgp_hodlr_import_top(bgp_hodlr_t* h, const double* all_buf_dev, int64_t rows_pad);
+/* row range [row0, row0+rows) owned by shard `s` (same on every shard; -1 rows if the tree cannot be cut) */
+int bgp_hodlr_shard_rows(const bgp_hodlr_t* h, int32_t s, int64_t* row0, int64_t* rows);
 int bgp_hodlr_finish_top(bgp_hodlr_t* h);
 /* sharded solve: local part, then (host all-gathers the vector), then top part. */
 int bgp_hodlr_solve_local_dev(bgp_hodlr_t* h, double* b_dev, int64_t nrhs, int64_t ldb);
