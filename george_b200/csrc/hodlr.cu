@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "hodlr_kernels.cuh"
+#include "hodlr_aca2.cuh"
 #include "kernel_eval.cuh"
 
 namespace bgp {
@@ -63,6 +64,12 @@ struct bgp_hodlr {
   DevBuf<NodeDesc> d_nodes;
   DevBuf<int> d_idx, d_piv_rows, d_piv_cols, d_ticket, d_chain_done, d_ncols_by_depth;
   DevBuf<uint32_t> d_chain_state;
+  DevBuf<A2Node> d_a2nodes;
+  DevBuf<A2State> d_a2states;
+  DevBuf<A2EPart> d_epart;
+  DevBuf<int> d_cand, d_cand_k, d_cand_words, d_cchunk_node, d_rchunk_node, d_nactive;
+  DevBuf<double> d_vpart, d_upart;
+  int aca_iters = 0;
   size_t w_cap = 0;
 
   double t_ms[5] = {0, 0, 0, 0, 0};
@@ -141,6 +148,91 @@ static int launch_level(bgp_hodlr* h, const LevelInfo& L, double* X, int64_t ldx
     dim3 grid((max_nh + UP_ROWS - 1) / UP_ROWS, nn * 2, (col_hi - col_lo + UP_TC - 1) / UP_TC);
     update_nn_kernel<<<grid, UP_THREADS, 0, s>>>(nd, h->d_U.p, h->n, X, ldx, col_lo, col_hi, h->d_W.p, stride, 0);
     BGP_LAUNCH_CHECK();
+  }
+  return BGP_OK;
+}
+
+// GPU-wide lock-step ACA (hodlr_aca2.cuh).  descs are in launch order; results go to houts[desc.node].
+static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector<AcaOut>& houts, cudaStream_t s) {
+  const int nn = (int)descs.size();
+  if (nn == 0) return BGP_OK;
+  std::vector<A2Node> hn(nn);
+  std::vector<int> cchunk_node, rchunk_node;
+  int64_t cand_total = 0, epart_total = 0;
+  int capmax = 1;
+  for (int i = 0; i < nn; ++i) {
+    const AcaDesc& d = descs[i];
+    A2Node& a = hn[i];
+    a.row0 = d.row0; a.n_rows = d.n_rows; a.col0 = d.col0; a.n_cols = d.n_cols;
+    a.vcol = d.vcol; a.cap = d.cap; a.pre_id = d.pre_id; a.node = d.node;
+    a.idx_off = d.idx_off; a.piv_off = d.piv_off;
+    a.cchunk0 = (int)cchunk_node.size(); a.n_cchunks = (d.n_cols + A2_CHUNK - 1) / A2_CHUNK;
+    a.rchunk0 = (int)rchunk_node.size(); a.n_rchunks = (d.n_rows + A2_CHUNK - 1) / A2_CHUNK;
+    for (int c = 0; c < a.n_cchunks; ++c) cchunk_node.push_back(i);
+    for (int c = 0; c < a.n_rchunks; ++c) rchunk_node.push_back(i);
+    a.bmax = std::min(A2_BMAX, d.n_rows); a._pad = 0;
+    a.cand_off = cand_total; cand_total += a.bmax;
+    a.epart_off = epart_total; epart_total += (int64_t)a.bmax * a.n_cchunks;
+    capmax = std::max(capmax, d.cap);
+  }
+  const int ncc = (int)cchunk_node.size(), nrc = (int)rchunk_node.size();
+  BGP_TRY(h->d_a2nodes.reserve(nn, s));
+  BGP_TRY(h->d_a2states.reserve(nn, s));
+  BGP_TRY(h->d_cand.reserve((size_t)cand_total, s));
+  BGP_TRY(h->d_cand_k.reserve((size_t)cand_total, s));
+  BGP_TRY(h->d_cand_words.reserve((size_t)cand_total, s));
+  BGP_TRY(h->d_epart.reserve((size_t)epart_total, s));
+  BGP_TRY(h->d_cchunk_node.reserve(ncc, s));
+  BGP_TRY(h->d_rchunk_node.reserve(nrc, s));
+  BGP_TRY(h->d_vpart.reserve((size_t)ncc * (capmax + 1), s));
+  BGP_TRY(h->d_upart.reserve((size_t)nrc * (capmax + 1), s));
+  BGP_TRY(h->d_nactive.reserve(1, s));
+  BGP_CUDA(cudaMemcpyAsync(h->d_a2nodes.p, hn.data(), sizeof(A2Node) * nn, cudaMemcpyHostToDevice, s));
+  BGP_CUDA(cudaMemcpyAsync(h->d_cchunk_node.p, cchunk_node.data(), sizeof(int) * ncc, cudaMemcpyHostToDevice, s));
+  BGP_CUDA(cudaMemcpyAsync(h->d_rchunk_node.p, rchunk_node.data(), sizeof(int) * nrc, cudaMemcpyHostToDevice, s));
+  BGP_CUDA(cudaMemcpyAsync(h->d_nactive.p, &nn, sizeof(int), cudaMemcpyHostToDevice, s));
+  A2Args a;
+  a.prog = h->d_prog.p; a.x = h->d_x.p; a.nodes = h->d_a2nodes.p; a.states = h->d_a2states.p; a.n_nodes = nn;
+  a.Vp = h->d_V.p; a.ld = h->n; a.tol = h->opts.tol; a.seed = (uint32_t)h->opts.seed; a.exhaust_mode = h->opts.exhaust_mode;
+  a.idx_ws = h->d_idx.p; a.piv_rows = h->d_piv_rows.p; a.piv_cols = h->d_piv_cols.p;
+  a.cand = h->d_cand.p; a.cand_k = h->d_cand_k.p; a.cand_words = h->d_cand_words.p; a.epart = h->d_epart.p;
+  a.cchunk_node = h->d_cchunk_node.p; a.rchunk_node = h->d_rchunk_node.p; a.vpart = h->d_vpart.p; a.upart = h->d_upart.p;
+  a.capmax = capmax; a.n_active = h->d_nactive.p;
+  a2_init_kernel<<<nn, 256, 0, s>>>(a);
+  BGP_LAUNCH_CHECK();
+  int active = nn, iters = 0;
+  while (active > 0) {
+    for (int rep = 0; rep < 8; ++rep) {
+      a2_eval_kernel<<<dim3(ncc, A2_GROUPS), A2_THREADS, 0, s>>>(a);
+      BGP_LAUNCH_CHECK();
+      a2_decide_kernel<<<nn, 128, 0, s>>>(a);
+      BGP_LAUNCH_CHECK();
+      a2_vnorm_kernel<<<ncc, A2_THREADS, 0, s>>>(a);
+      BGP_LAUNCH_CHECK();
+      a2_ucol_kernel<<<nrc, A2_THREADS, 0, s>>>(a);
+      BGP_LAUNCH_CHECK();
+      a2_finish_kernel<<<nn, 128, 0, s>>>(a);
+      BGP_LAUNCH_CHECK();
+      iters++;
+    }
+    BGP_CUDA(cudaMemcpyAsync(&active, h->d_nactive.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BGP_CUDA(cudaStreamSynchronize(s));
+    if (iters > (1 << 22)) { set_error("ACA did not terminate"); return BGP_ERR_CUDA; }
+  }
+  h->aca_iters = iters;
+  if (h->opts.exhaust_mode == BGP_EXHAUST_DENSE) {
+    a2_dense_fill_kernel<<<dim3(nn, 64), 256, 0, s>>>(a);
+    BGP_LAUNCH_CHECK();
+    a2_dense_rank_kernel<<<(nn + 127) / 128, 128, 0, s>>>(a);
+    BGP_LAUNCH_CHECK();
+  }
+  std::vector<A2State> hs(nn);
+  BGP_CUDA(cudaMemcpyAsync(hs.data(), h->d_a2states.p, sizeof(A2State) * nn, cudaMemcpyDeviceToHost, s));
+  BGP_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < nn; ++i) {
+    AcaOut o;
+    o.rank = hs[i].rank; o.draws = hs[i].draws; o.fallback = hs[i].fallback; o.status = hs[i].status;
+    houts[descs[i].node] = o;
   }
   return BGP_OK;
 }
@@ -295,7 +387,9 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
     BGP_TRY(h->d_chain_state.reserve(640, sB));
     BGP_TRY(h->d_chain_done.reserve(std::max(nint, 1), sB));
     houts.assign(nint, AcaOut());
-    if (nint) {
+    if (nint && o.rng_mode != BGP_RNG_REFERENCE) {
+      BGP_TRY(run_aca2(h, hdesc_sorted, houts, sB));
+    } else if (nint) {
       BGP_CUDA(cudaMemcpyAsync(h->d_aca.p, hdesc_sorted.data(), sizeof(AcaDesc) * nint, cudaMemcpyHostToDevice, sB));
       BGP_CUDA(cudaMemsetAsync(h->d_ticket.p, 0, sizeof(int), sB));
       BGP_CUDA(cudaMemsetAsync(h->d_chain_done.p, 0, sizeof(int) * nint, sB));
@@ -479,6 +573,9 @@ void bgp_hodlr_destroy(bgp_hodlr_t* h) {
   h->d_W.release(); h->d_scalar.release(); h->d_rhs.release(); h->d_leaves.release(); h->d_aca.release();
   h->d_aca_out.release(); h->d_nodes.release(); h->d_idx.release(); h->d_piv_rows.release(); h->d_piv_cols.release();
   h->d_ticket.release(); h->d_chain_done.release(); h->d_ncols_by_depth.release(); h->d_chain_state.release();
+  h->d_a2nodes.release(); h->d_a2states.release(); h->d_epart.release(); h->d_cand.release(); h->d_cand_k.release();
+  h->d_cand_words.release(); h->d_cchunk_node.release(); h->d_rchunk_node.release(); h->d_nactive.release();
+  h->d_vpart.release(); h->d_upart.release();
   if (h->sA) {
     cudaStreamSynchronize(h->sA); cudaStreamSynchronize(h->sB);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);

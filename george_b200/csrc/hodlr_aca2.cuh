@@ -1,0 +1,530 @@
+// hodlr_aca2.cuh — K5, GPU-wide version: every internal node's ACA advances in lock-step and each step's work is spread
+// over the whole chip as (node, chunk-of-1024-columns/rows) items.
+//
+// Same algorithm as hodlr.h:136-221 (and as aca_kernel in hodlr_kernels.cuh, which is kept for the chained
+// rng_mode = reference): random row -> residual -> arg-max pivot -> retry while |pivot| < 1e-14 -> column residual ->
+// stopping rule.  What changes is the schedule:
+//   * while a node looks for a usable pivot row, the factors do not change, so the next B candidate rows of its RNG
+//     sequence are evaluated SPECULATIVELY in one launch; the first candidate (in sequence order) with
+//     max|residual| >= 1e-14 wins and the RNG / row-index list are committed up to exactly that draw — bit-identical
+//     to the one-at-a-time loop.  B doubles after a fully rejected batch.  Kernels that are exactly low rank
+//     (Matern-3/2 in 1-D) reject EVERY row of most nodes; this turns that O(n_rows * n_cols) scan into a dense,
+//     perfectly parallel evaluation instead of n_rows dependent steps.
+//   * one iteration = 5 small launches shared by all nodes:  eval -> decide -> vnorm -> ucol -> finish.
+#pragma once
+
+#include "hodlr_kernels.cuh"
+
+namespace bgp {
+
+constexpr int A2_CHUNK = 1024;    // rows / columns per work item
+constexpr int A2_THREADS = 256;
+constexpr int A2_EPT = A2_CHUNK / A2_THREADS;  // elements per thread
+constexpr int A2_CG = 8;          // candidates evaluated together (register blocking)
+constexpr int A2_GROUPS = 4;      // candidate groups (gridDim.y of the eval kernel)
+constexpr int A2_BMAX = 2048;     // max speculative candidates per iteration
+
+struct A2Node {  // static description
+  int row0, n_rows, col0, n_cols;
+  int vcol, cap, pre_id, node;
+  int cchunk0, n_cchunks, rchunk0, n_rchunks;
+  int bmax, _pad;
+  int64_t idx_off, piv_off, cand_off, epart_off;
+};
+
+struct A2State {  // dynamic
+  int rank, draws, n_index, fallback, status, active;
+  int phase;  // 0 = candidates pending evaluation, 1 = pivot accepted (vnorm/ucol run), 2 = done
+  int B, ncand, piv_i, piv_j, _pad;
+  double pivot, norm;
+  MT19937 rng;  // committed stream
+};
+
+struct A2EPart {
+  double val;  // signed residual entry of largest magnitude in (candidate, chunk)
+  int idx;     // its column (block-relative), lowest on ties
+  int _pad;
+};
+
+enum { A2_SELECT = 0, A2_ACCEPT = 1, A2_DONE = 2 };
+
+// draw up to B candidate rows speculatively (thread 0).  cand[c] = row, cand_k[c] = position drawn, words[c] = mt19937
+// words consumed up to and including draw c.  The index list is modified (swap-pop) and undone later if needed.
+__device__ inline void a2_generate(A2State& st, MT19937& spec, int* index, int* cand, int* cand_k, int* words, int bmax) {
+  const int B = min(min(st.B, bmax), st.n_index);
+  int w = 0;
+  int n_index = st.n_index;
+  for (int c = 0; c < B; ++c) {
+    const int k = mt_uniform(spec, (uint32_t)n_index, &w);
+    cand[c] = index[k];
+    cand_k[c] = k;
+    words[c] = w;
+    index[k] = index[n_index - 1];
+    n_index--;
+  }
+  st.ncand = B;
+}
+
+// cooperative 625-word copy of an mt19937 state (all threads of the CTA; caller synchronises)
+__device__ __forceinline__ void mt_copy(MT19937* dst, const MT19937* src) {
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+  for (int i = threadIdx.x; i < (int)(sizeof(MT19937) / 4); i += blockDim.x) d[i] = s[i];
+}
+
+struct A2Args {
+  const DevProgram* prog;
+  const double* x;
+  const A2Node* nodes;
+  A2State* states;
+  int n_nodes;
+  double* Vp;
+  int64_t ld;
+  double tol;
+  uint32_t seed;
+  int exhaust_mode;
+  int* idx_ws;
+  int* piv_rows;
+  int* piv_cols;
+  int* cand;       // candidate rows          [cand_off + c]
+  int* cand_k;     // drawn positions
+  int* cand_words; // cumulative words
+  A2EPart* epart;  // [epart_off + c * n_cchunks + chunk]
+  const int* cchunk_node;  // chunk -> node
+  const int* rchunk_node;
+  double* vpart;   // per column chunk: [chunk * (capmax + 1)] : vn2 then dots[k]
+  double* upart;   // per row chunk
+  int capmax;
+  int* n_active;
+};
+
+// ---- init: index list, RNG seed, first candidates -------------------------------------------------------------
+__global__ void __launch_bounds__(256) a2_init_kernel(A2Args a) {
+  __shared__ MT19937 rng;
+  const int nid = blockIdx.x;
+  const A2Node nd = a.nodes[nid];
+  A2State& st = a.states[nid];
+  int* index = a.idx_ws + nd.idx_off;
+  for (int n = threadIdx.x; n < nd.n_rows; n += blockDim.x) index[n] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mt_seed(rng, node_seed(a.seed, nd.pre_id));
+    st.rank = 0; st.draws = 0; st.n_index = nd.n_rows; st.fallback = 0; st.status = 0; st.active = 1;
+    st.phase = A2_SELECT; st.B = 4; st.norm = 0.0; st.pivot = 0.0; st.piv_i = 0; st.piv_j = 0;
+  }
+  __syncthreads();
+  mt_copy(&st.rng, &rng);  // committed = state before the speculative draws
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (nd.cap <= 0) { st.status = 1; st.phase = A2_DONE; st.active = 0; atomicSub(a.n_active, 1); }
+    else a2_generate(st, rng, index, a.cand + nd.cand_off, a.cand_k + nd.cand_off, a.cand_words + nd.cand_off, nd.bmax);
+  }
+}
+
+// ---- eval: residual maxima of the pending candidate rows ------------------------------------------------------
+__global__ void __launch_bounds__(A2_THREADS) a2_eval_kernel(A2Args a) {
+  __shared__ DevProgram P;
+  __shared__ double s_x[A2_CG][ACA_MAX_NDIM];
+  __shared__ double s_u[A2_CG][128 + 1];  // U(i, k) for a k-tile of 128
+  __shared__ double s_red[A2_CG][A2_THREADS / 32];
+  __shared__ int s_redi[A2_CG][A2_THREADS / 32];
+  const int chunk = blockIdx.x;
+  const int nid = a.cchunk_node[chunk];
+  const A2State& st = a.states[nid];
+  if (st.phase != A2_SELECT || !st.active) return;
+  const int ncand = st.ncand;
+  if (ncand <= (int)blockIdx.y * A2_CG) return;
+  const A2Node nd = a.nodes[nid];
+  stage_program(&P, a.prog);
+  const int ndim = a.prog->ndim;
+  const int rank = st.rank;
+  const int lc = chunk - nd.cchunk0;
+  const int c_lo = lc * A2_CHUNK;
+  const int c_n = min(A2_CHUNK, nd.n_cols - c_lo);
+  const double* Vcols = a.Vp + (int64_t)nd.vcol * a.ld;
+  const double* xr = a.x + (int64_t)nd.row0 * ndim;
+  const double* xc = a.x + (int64_t)(nd.col0 + c_lo) * ndim;
+  const int* cand = a.cand + nd.cand_off;
+  A2EPart* ep = a.epart + nd.epart_off;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+
+  for (int cb = blockIdx.y * A2_CG; cb < ncand; cb += A2_GROUPS * A2_CG) {
+    const int ncb = min(A2_CG, ncand - cb);
+    double vals[A2_CG][A2_EPT];
+    __syncthreads();
+    for (int t = threadIdx.x; t < A2_CG * ndim; t += A2_THREADS) {
+      const int c = t / ndim, q = t % ndim;
+      s_x[c][q] = (c < ncb) ? xr[(int64_t)cand[cb + c] * ndim + q] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < A2_EPT; ++e) {
+      const int n = threadIdx.x + e * A2_THREADS;
+      if (n < c_n) {
+#pragma unroll
+        for (int c = 0; c < A2_CG; ++c) vals[c][e] = (c < ncb) ? kernel_value(P, s_x[c], xc + (int64_t)n * ndim) : 0.0;
+      } else {
+#pragma unroll
+        for (int c = 0; c < A2_CG; ++c) vals[c][e] = 0.0;
+      }
+    }
+    for (int k0 = 0; k0 < rank; k0 += 128) {
+      const int nk = min(128, rank - k0);
+      __syncthreads();
+      for (int t = threadIdx.x; t < A2_CG * nk; t += A2_THREADS) {
+        const int c = t / nk, k = t % nk;
+        s_u[c][k] = (c < ncb) ? __ldcg(Vcols + (int64_t)(k0 + k) * a.ld + nd.row0 + cand[cb + c]) : 0.0;
+      }
+      __syncthreads();
+      for (int k = 0; k < nk; ++k) {
+        double vk[A2_EPT];
+#pragma unroll
+        for (int e = 0; e < A2_EPT; ++e) {
+          const int n = threadIdx.x + e * A2_THREADS;
+          vk[e] = (n < c_n) ? Vcols[(int64_t)(k0 + k) * a.ld + nd.col0 + c_lo + n] : 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < A2_CG; ++c) {
+          const double u = s_u[c][k];
+#pragma unroll
+          for (int e = 0; e < A2_EPT; ++e) vals[c][e] -= u * vk[e];
+        }
+      }
+    }
+    // per-candidate arg-max over the chunk
+#pragma unroll
+    for (int c = 0; c < A2_CG; ++c) {
+      double best = -1.0, bval = 0.0;
+      int bidx = 0x7fffffff;
+#pragma unroll
+      for (int e = 0; e < A2_EPT; ++e) {
+        const int n = threadIdx.x + e * A2_THREADS;
+        const double av = fabs(vals[c][e]);
+        if (n < c_n && av > best) { best = av; bidx = c_lo + n; bval = vals[c][e]; }
+      }
+      // warp arg-max carrying the signed value
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const double ov = __shfl_xor_sync(0xffffffffu, bval, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; bval = ov; }
+      }
+      if (lane == 0) { s_red[c][warp] = bval; s_redi[c][warp] = bidx; }
+    }
+    __syncthreads();
+    if (threadIdx.x < ncb) {
+      const int c = threadIdx.x;
+      double bval = s_red[c][0];
+      int bidx = s_redi[c][0];
+      for (int w = 1; w < A2_THREADS / 32; ++w) {
+        const double ov = s_red[c][w];
+        const int oi = s_redi[c][w];
+        if (fabs(ov) > fabs(bval) || (fabs(ov) == fabs(bval) && oi < bidx)) { bval = ov; bidx = oi; }
+      }
+      A2EPart p;
+      p.val = bval; p.idx = bidx; p._pad = 0;
+      ep[(int64_t)(cb + c) * nd.n_cchunks + lc] = p;
+    }
+  }
+}
+
+// ---- decide: first usable candidate wins; commit the RNG / index list up to it ----------------------------------
+__global__ void __launch_bounds__(128) a2_decide_kernel(A2Args a) {
+  __shared__ MT19937 rng;
+  __shared__ int s_winner;
+  __shared__ double s_val[128];
+  __shared__ int s_idx[128];
+  const int nid = blockIdx.x;
+  A2State& st = a.states[nid];
+  if (st.phase != A2_SELECT || !st.active) return;
+  const A2Node nd = a.nodes[nid];
+  const int ncand = st.ncand;
+  const A2EPart* ep = a.epart + nd.epart_off;
+  int* cand = a.cand + nd.cand_off;
+  int* cand_k = a.cand_k + nd.cand_off;
+  int* words = a.cand_words + nd.cand_off;
+  int* index = a.idx_ws + nd.idx_off;
+  if (threadIdx.x == 0) s_winner = 0x7fffffff;
+  __syncthreads();
+  // candidates in blocks of 128, in order; stop at the first block containing a winner
+  for (int c0 = 0; c0 < ncand; c0 += 128) {
+    const int c = c0 + threadIdx.x;
+    double bval = 0.0;
+    int bidx = 0x7fffffff;
+    if (c < ncand) {
+      for (int ch = 0; ch < nd.n_cchunks; ++ch) {
+        const A2EPart p = ep[(int64_t)c * nd.n_cchunks + ch];
+        if (fabs(p.val) > fabs(bval) || (fabs(p.val) == fabs(bval) && p.idx < bidx)) { bval = p.val; bidx = p.idx; }
+      }
+      if (!(fabs(bval) < 1e-14)) atomicMin(&s_winner, c);  // hodlr.h:191 (NaN also leaves the loop, as in the reference)
+    }
+    s_val[threadIdx.x] = bval;
+    s_idx[threadIdx.x] = bidx;
+    __syncthreads();
+    if (s_winner != 0x7fffffff) break;
+    __syncthreads();
+  }
+  const int p = s_winner;
+  // commit the stream: replay exactly the words consumed up to the winner (or the whole batch)
+  mt_copy(&rng, &st.rng);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int w = (p != 0x7fffffff) ? words[p] : (ncand > 0 ? words[ncand - 1] : 0);
+    for (int q = 0; q < w; ++q) (void)mt_next(rng);
+    st.draws += w;
+  }
+  __syncthreads();
+  mt_copy(&st.rng, &rng);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (p != 0x7fffffff) {
+      // undo the speculative swap-pops beyond the winner, newest first
+      for (int c = ncand - 1; c > p; --c) index[cand_k[c]] = cand[c];
+      st.n_index -= (p + 1);
+      st.piv_i = cand[p];
+      st.piv_j = s_idx[p & 127];
+      st.pivot = s_val[p & 127];
+      st.phase = A2_ACCEPT;
+      st.B = max(1, min(st.B, 2 * (p + 1)));
+    } else {
+      st.n_index -= ncand;
+      st.B = min(2 * st.B, A2_BMAX);
+      if (st.n_index == 0) {
+        st.fallback = 1;  // rows exhausted (hodlr.h:161); dense fill (if requested) happens after the loop
+        st.phase = A2_DONE; st.active = 0;
+        atomicSub(a.n_active, 1);
+      } else {
+        a2_generate(st, rng, index, cand, cand_k, words, nd.bmax);
+      }
+    }
+  }
+}
+
+// ---- vnorm: normalised row residual -> panel column `rank`, partial ||v||^2 and V_prev^T v ----------------------
+__global__ void __launch_bounds__(A2_THREADS) a2_vnorm_kernel(A2Args a) {
+  __shared__ DevProgram P;
+  __shared__ double s_x[ACA_MAX_NDIM];
+  __shared__ double s_u[128];
+  __shared__ double s_v[A2_CHUNK];
+  __shared__ double red[32];
+  const int chunk = blockIdx.x;
+  const int nid = a.cchunk_node[chunk];
+  const A2State& st = a.states[nid];
+  if (st.phase != A2_ACCEPT || !st.active) return;
+  const A2Node nd = a.nodes[nid];
+  stage_program(&P, a.prog);
+  const int ndim = a.prog->ndim;
+  const int rank = st.rank;
+  const int lc = chunk - nd.cchunk0;
+  const int c_lo = lc * A2_CHUNK;
+  const int c_n = min(A2_CHUNK, nd.n_cols - c_lo);
+  double* Vcols = a.Vp + (int64_t)nd.vcol * a.ld;
+  const double* xc = a.x + (int64_t)(nd.col0 + c_lo) * ndim;
+  const int i = st.piv_i;
+  const double pivot = st.pivot;
+  for (int q = threadIdx.x; q < ndim; q += A2_THREADS) s_x[q] = a.x[(int64_t)(nd.row0 + i) * ndim + q];
+  __syncthreads();
+  double vals[A2_EPT];
+#pragma unroll
+  for (int e = 0; e < A2_EPT; ++e) {
+    const int n = threadIdx.x + e * A2_THREADS;
+    vals[e] = (n < c_n) ? kernel_value(P, s_x, xc + (int64_t)n * ndim) : 0.0;
+  }
+  for (int k0 = 0; k0 < rank; k0 += 128) {
+    const int nk = min(128, rank - k0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < nk; k += A2_THREADS) s_u[k] = __ldcg(Vcols + (int64_t)(k0 + k) * a.ld + nd.row0 + i);
+    __syncthreads();
+    for (int k = 0; k < nk; ++k) {
+      const double u = s_u[k];
+#pragma unroll
+      for (int e = 0; e < A2_EPT; ++e) {
+        const int n = threadIdx.x + e * A2_THREADS;
+        if (n < c_n) vals[e] -= u * Vcols[(int64_t)(k0 + k) * a.ld + nd.col0 + c_lo + n];
+      }
+    }
+  }
+  double vn2 = 0.0;
+#pragma unroll
+  for (int e = 0; e < A2_EPT; ++e) {
+    const int n = threadIdx.x + e * A2_THREADS;
+    if (n < c_n) {
+      const double v = vals[e] / pivot;  // hodlr.h:194
+      Vcols[(int64_t)rank * a.ld + nd.col0 + c_lo + n] = v;
+      s_v[n] = v;
+      vn2 += v * v;
+    }
+  }
+  vn2 = block_sum(vn2, red);
+  double* part = a.vpart + (int64_t)chunk * (a.capmax + 1);
+  if (threadIdx.x == 0) part[0] = vn2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = warp; k < rank; k += A2_THREADS / 32) {
+    const double* vk = Vcols + (int64_t)k * a.ld + nd.col0 + c_lo;
+    double s = 0.0;
+    for (int n = lane; n < c_n; n += 32) s += vk[n] * s_v[n];
+    s = warp_sum(s);
+    if (lane == 0) part[1 + k] = s;
+  }
+}
+
+// ---- ucol: column residual -> panel column `rank` (row part), partial ||u||^2 and U_prev^T u --------------------
+__global__ void __launch_bounds__(A2_THREADS) a2_ucol_kernel(A2Args a) {
+  __shared__ DevProgram P;
+  __shared__ double s_x[ACA_MAX_NDIM];
+  __shared__ double s_vr[128];
+  __shared__ double s_u[A2_CHUNK];
+  __shared__ double red[32];
+  const int chunk = blockIdx.x;
+  const int nid = a.rchunk_node[chunk];
+  const A2State& st = a.states[nid];
+  if (st.phase != A2_ACCEPT || !st.active) return;
+  const A2Node nd = a.nodes[nid];
+  stage_program(&P, a.prog);
+  const int ndim = a.prog->ndim;
+  const int rank = st.rank;
+  const int lr = chunk - nd.rchunk0;
+  const int r_lo = lr * A2_CHUNK;
+  const int r_n = min(A2_CHUNK, nd.n_rows - r_lo);
+  double* Vcols = a.Vp + (int64_t)nd.vcol * a.ld;
+  const double* xr = a.x + (int64_t)(nd.row0 + r_lo) * ndim;
+  const int j = st.piv_j;
+  for (int q = threadIdx.x; q < ndim; q += A2_THREADS) s_x[q] = a.x[(int64_t)(nd.col0 + j) * ndim + q];
+  __syncthreads();
+  double vals[A2_EPT];
+#pragma unroll
+  for (int e = 0; e < A2_EPT; ++e) {
+    const int n = threadIdx.x + e * A2_THREADS;
+    vals[e] = (n < r_n) ? kernel_value(P, xr + (int64_t)n * ndim, s_x) : 0.0;
+  }
+  for (int k0 = 0; k0 < rank; k0 += 128) {
+    const int nk = min(128, rank - k0);
+    __syncthreads();
+    // V(j, k) for k < rank: columns already normalised in earlier iterations
+    for (int k = threadIdx.x; k < nk; k += A2_THREADS) s_vr[k] = __ldcg(Vcols + (int64_t)(k0 + k) * a.ld + nd.col0 + j);
+    __syncthreads();
+    for (int k = 0; k < nk; ++k) {
+      const double v = s_vr[k];
+#pragma unroll
+      for (int e = 0; e < A2_EPT; ++e) {
+        const int n = threadIdx.x + e * A2_THREADS;
+        if (n < r_n) vals[e] -= v * Vcols[(int64_t)(k0 + k) * a.ld + nd.row0 + r_lo + n];
+      }
+    }
+  }
+  double un2 = 0.0;
+#pragma unroll
+  for (int e = 0; e < A2_EPT; ++e) {
+    const int n = threadIdx.x + e * A2_THREADS;
+    if (n < r_n) {
+      Vcols[(int64_t)rank * a.ld + nd.row0 + r_lo + n] = vals[e];
+      s_u[n] = vals[e];
+      un2 += vals[e] * vals[e];
+    }
+  }
+  un2 = block_sum(un2, red);
+  double* part = a.upart + (int64_t)chunk * (a.capmax + 1);
+  if (threadIdx.x == 0) part[0] = un2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = warp; k < rank; k += A2_THREADS / 32) {
+    const double* uk = Vcols + (int64_t)k * a.ld + nd.row0 + r_lo;
+    double s = 0.0;
+    for (int n = lane; n < r_n; n += 32) s += uk[n] * s_u[n];
+    s = warp_sum(s);
+    if (lane == 0) part[1 + k] = s;
+  }
+}
+
+// ---- finish: stopping rule (hodlr.h:202-214), next candidates -----------------------------------------------------
+__global__ void __launch_bounds__(128) a2_finish_kernel(A2Args a) {
+  __shared__ MT19937 rng;
+  __shared__ double red[32];
+  const int nid = blockIdx.x;
+  A2State& st = a.states[nid];
+  if (st.phase != A2_ACCEPT || !st.active) return;
+  const A2Node nd = a.nodes[nid];
+  const int rank = st.rank;
+  double vn2 = 0.0, un2 = 0.0;
+  for (int c = threadIdx.x; c < nd.n_cchunks; c += blockDim.x) vn2 += a.vpart[(int64_t)(nd.cchunk0 + c) * (a.capmax + 1)];
+  for (int c = threadIdx.x; c < nd.n_rchunks; c += blockDim.x) un2 += a.upart[(int64_t)(nd.rchunk0 + c) * (a.capmax + 1)];
+  vn2 = block_sum(vn2, red);
+  un2 = block_sum(un2, red);
+  double vdot = 0.0, udot = 0.0;
+  for (int k = threadIdx.x; k < rank; k += blockDim.x) {
+    double sv = 0.0, su = 0.0;
+    for (int c = 0; c < nd.n_cchunks; ++c) sv += a.vpart[(int64_t)(nd.cchunk0 + c) * (a.capmax + 1) + 1 + k];
+    for (int c = 0; c < nd.n_rchunks; ++c) su += a.upart[(int64_t)(nd.rchunk0 + c) * (a.capmax + 1) + 1 + k];
+    vdot = fmax(vdot, fabs(sv));
+    udot = fmax(udot, fabs(su));
+  }
+  vdot = block_max(vdot, red);
+  udot = block_max(udot, red);
+  mt_copy(&rng, &st.rng);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a.piv_rows[nd.piv_off + rank] = st.piv_i;
+    a.piv_cols[nd.piv_off + rank] = st.piv_j;
+    const int new_rank = rank + 1;
+    st.rank = new_rank;
+    const int max_rank = min(nd.n_rows, nd.n_cols);
+    bool done = false;
+    if (new_rank >= max_rank) done = true;  // hodlr.h:203
+    else {
+      const double rowcol = un2 * vn2;
+      if (rowcol < a.tol * a.tol * st.norm) done = true;  // hodlr.h:207
+      else {
+        st.norm += rowcol;
+        if (new_rank > 1) st.norm += 2.0 * udot + 2.0 * vdot;
+        if (new_rank >= nd.cap) { st.status = 1; done = true; }       // no room for another column
+        else if (st.n_index == 0) { st.fallback = 1; done = true; }  // next pass of the do-loop would find no rows
+      }
+    }
+    if (done) {
+      st.phase = A2_DONE; st.active = 0;
+      atomicSub(a.n_active, 1);
+    } else {
+      st.phase = A2_SELECT;
+      a2_generate(st, rng, a.idx_ws + nd.idx_off, a.cand + nd.cand_off, a.cand_k + nd.cand_off, a.cand_words + nd.cand_off,
+                  nd.bmax);
+    }
+  }
+}
+
+// ---- dense fallback fill (hodlr.h:161-176): V = I, U = K(rows, cols) ---------------------------------------------
+// grid = (node, column m); nodes without the fallback flag (or in low-rank exhaust mode) return at once.
+__global__ void __launch_bounds__(256) a2_dense_fill_kernel(A2Args a) {
+  __shared__ DevProgram P;
+  const int nid = blockIdx.x;
+  A2State& st = a.states[nid];
+  if (!st.fallback || a.exhaust_mode != BGP_EXHAUST_DENSE || st.status) return;
+  const A2Node nd = a.nodes[nid];
+  const int max_rank = min(nd.n_rows, nd.n_cols);
+  if (max_rank > nd.cap) {
+    if (blockIdx.y == 0 && threadIdx.x == 0) st.status = 1;
+    return;
+  }
+  stage_program(&P, a.prog);
+  __syncthreads();
+  const int ndim = P.ndim;
+  const double* xr = a.x + (int64_t)nd.row0 * ndim;
+  const double* xc = a.x + (int64_t)nd.col0 * ndim;
+  for (int m = blockIdx.y; m < nd.n_cols; m += gridDim.y) {
+    double* vc = a.Vp + (int64_t)(nd.vcol + m) * a.ld;
+    for (int n = threadIdx.x; n < nd.n_cols; n += blockDim.x) vc[nd.col0 + n] = (n == m) ? 1.0 : 0.0;
+    for (int n = threadIdx.x; n < nd.n_rows; n += blockDim.x)
+      vc[nd.row0 + n] = kernel_value(P, xr + (int64_t)n * ndim, xc + (int64_t)m * ndim);
+  }
+}
+__global__ void a2_dense_rank_kernel(A2Args a) {
+  const int nid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nid >= a.n_nodes) return;
+  A2State& st = a.states[nid];
+  if (st.fallback && a.exhaust_mode == BGP_EXHAUST_DENSE && !st.status) {
+    const A2Node nd = a.nodes[nid];
+    st.rank = min(nd.n_rows, nd.n_cols);
+  }
+}
+
+}  // namespace bgp

@@ -35,6 +35,7 @@ if __name__ == "__main__":
     ap.add_argument("--n", type=int, default=65536)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--tol", type=float, default=None)
+    ap.add_argument("--exhaust", default="dense")
     a = ap.parse_args()
     k, x, yerr, y, kw = make(a.cfg, a.n)
     if a.tol is not None:
@@ -42,7 +43,7 @@ if __name__ == "__main__":
     s = HODLRSolver()
     for rep in range(a.reps):
         t0 = time.perf_counter()
-        s.compute(k, x, yerr, seed=42, **kw)
+        s.compute(k, x, yerr, seed=42, exhaust=a.exhaust, **kw)
         t1 = time.perf_counter()
         d = s.dot_solve(y)
         t2 = time.perf_counter()
