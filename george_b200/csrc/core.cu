@@ -161,6 +161,16 @@ int build_dev_program(const bgp_kernel_spec_t* s, DevProgram* P) {
   if (max_depth > BGP_STACK) { set_error("kernel expression too deep for the device interpreter (%d > %d)", max_depth, BGP_STACK); return BGP_ERR_INVALID; }
   P->n_leaves = nl;
   P->n_params_total = off;
+  // fast 1-D path: every leaf is a function of d = x1 - x2 alone
+  bool fast = (s->ndim == 1);
+  for (int i = 0; i < nl && fast; ++i) {
+    const DevLeaf& L = P->leaf[i];
+    const int kt = L.kernel_type;
+    if (L.naxes != 1 || L.axes[0] != 0) fast = false;
+    else if (is_stationary(kt)) fast = (L.metric_type != BGP_METRIC_GENERAL) && !L.blocked;
+    else fast = (kt == BGP_K_EXP_SINE2 || kt == BGP_K_COSINE || kt == BGP_K_CONSTANT);
+  }
+  P->flags = fast ? 1 : 0;
   return BGP_OK;
 }
 

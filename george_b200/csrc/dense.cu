@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "gemm_dmma.cuh"
 #include "kernel_eval.cuh"
 
 namespace bgp {
@@ -16,7 +17,8 @@ int upload_program(const DevProgram& P, DevBuf<DevProgram>& buf, cudaStream_t s)
 int kmat_symmetric_launch(const DevProgram* dprog, int nd, const double* x, int64_t n, const double* diag_add,
                           double* out, int64_t ld, cudaStream_t s);
 
-constexpr int DN_NB = 64;  // panel width
+constexpr int DN_NB = 64;   // inner panel width (diagonal block in shared memory)
+constexpr int DN_OB = 256;  // outer block: trailing updates beyond it run with K = 256 on the tensor pipe
 
 // ---- diagonal block Cholesky (NB x NB) in shared memory; info != 0 when a pivot is not positive ------------------
 __global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ A, int64_t lda, int nb, int* info, int k0) {
@@ -227,6 +229,7 @@ struct bgp_dense {
   DevBuf<DevProgram> d_prog;
   DevBuf<double> d_x, d_yerr, d_diag, d_A, d_rhs, d_scalar;
   DevBuf<int> d_info;
+  DevBuf<GemmDesc> d_gdesc;
   double t_ms[2] = {0, 0};
 };
 
@@ -234,20 +237,55 @@ static int dense_potrf(bgp_dense* h) {
   const int64_t n = h->n;
   double* A = h->d_A.p;
   cudaStream_t s = h->s;
-  for (int64_t k0 = 0; k0 < n; k0 += DN_NB) {
-    const int nb = (int)std::min<int64_t>(DN_NB, n - k0);
-    double* Akk = A + k0 * n + k0;
-    potf2_kernel<<<1, 256, 0, s>>>(Akk, n, nb, h->d_info.p, (int)k0);
+  // all trailing-update descriptors of the factorisation, uploaded once
+  std::vector<GemmDesc> descs;
+  struct Step { int64_t k0; int nb; int64_t rem; int inner_desc, outer_desc; };
+  std::vector<Step> steps;
+  for (int64_t J0 = 0; J0 < n; J0 += DN_OB) {
+    const int ob = (int)std::min<int64_t>(DN_OB, n - J0);
+    for (int64_t j0 = J0; j0 < J0 + ob; j0 += DN_NB) {
+      Step st;
+      st.k0 = j0; st.nb = (int)std::min<int64_t>(DN_NB, J0 + ob - j0); st.rem = n - j0 - st.nb;
+      st.inner_desc = -1; st.outer_desc = -1;
+      const int64_t nc = J0 + ob - (j0 + st.nb);
+      if (st.rem > 0 && nc > 0) {
+        GemmDesc d;
+        const double* P = A + j0 * n + j0 + st.nb;  // rows below the diagonal block, nb columns
+        d.A = P; d.lda = n; d.B = P; d.ldb = n;     // B' = P^T restricted to the first nc rows of P
+        d.C = A + (j0 + st.nb) * n + j0 + st.nb; d.ldc = n;
+        d.M = (int)st.rem; d.N = (int)nc; d.K = st.nb; d.mode = GD_SUB | GD_LOWER;
+        st.inner_desc = (int)descs.size();
+        descs.push_back(d);
+      }
+      if (j0 + st.nb >= J0 + ob) {  // last inner step of this outer block: big trailing update
+        const int64_t rem2 = n - J0 - ob;
+        if (rem2 > 0) {
+          GemmDesc d;
+          const double* P = A + J0 * n + J0 + ob;
+          d.A = P; d.lda = n; d.B = P; d.ldb = n;
+          d.C = A + (J0 + ob) * n + J0 + ob; d.ldc = n;
+          d.M = (int)rem2; d.N = (int)rem2; d.K = ob; d.mode = GD_SUB | GD_LOWER;
+          st.outer_desc = (int)descs.size();
+          descs.push_back(d);
+        }
+      }
+      steps.push_back(st);
+    }
+  }
+  BGP_TRY(h->d_gdesc.reserve(std::max<size_t>(descs.size(), 1), s));
+  if (!descs.empty())
+    BGP_CUDA(cudaMemcpyAsync(h->d_gdesc.p, descs.data(), sizeof(GemmDesc) * descs.size(), cudaMemcpyHostToDevice, s));
+  for (const Step& st : steps) {
+    double* Akk = A + st.k0 * n + st.k0;
+    potf2_kernel<<<1, 256, 0, s>>>(Akk, n, st.nb, h->d_info.p, (int)st.k0);
     BGP_LAUNCH_CHECK();
-    const int64_t rem = n - k0 - nb;
-    if (rem <= 0) break;
-    trsm_panel_kernel<<<(unsigned)((rem + 127) / 128), 128, 0, s>>>(Akk, n, rem, nb, h->d_info.p);
+    if (st.rem <= 0) break;
+    trsm_panel_kernel<<<(unsigned)((st.rem + 127) / 128), 128, 0, s>>>(Akk, n, st.rem, st.nb, h->d_info.p);
     BGP_LAUNCH_CHECK();
-    const unsigned nt = (unsigned)((rem + GM_T - 1) / GM_T);
-    dim3 grid(nt, nt);
-    const double* A21 = Akk + nb;
-    gemm_sub_kernel<0, 1><<<grid, 256, 0, s>>>(rem, rem, nb, A21, n, A21, n, Akk + (int64_t)nb * n + nb, n, 1, h->d_info.p);
-    BGP_LAUNCH_CHECK();
+    if (st.inner_desc >= 0)
+      BGP_TRY((gemm_dmma_launch<false, false>(h->d_gdesc.p + st.inner_desc, 1, descs[st.inner_desc].M, descs[st.inner_desc].N, h->d_info.p, s)));
+    if (st.outer_desc >= 0)
+      BGP_TRY((gemm_dmma_launch<false, false>(h->d_gdesc.p + st.outer_desc, 1, descs[st.outer_desc].M, descs[st.outer_desc].N, h->d_info.p, s)));
   }
   return BGP_OK;
 }
@@ -294,7 +332,7 @@ void bgp_dense_destroy(bgp_dense_t* h) {
   if (!h) return;
   if (h->s) cudaStreamSynchronize(h->s);
   h->d_prog.release(); h->d_x.release(); h->d_yerr.release(); h->d_diag.release(); h->d_A.release();
-  h->d_rhs.release(); h->d_scalar.release(); h->d_info.release();
+  h->d_rhs.release(); h->d_scalar.release(); h->d_info.release(); h->d_gdesc.release();
   if (h->s) {
     cudaStreamSynchronize(h->s);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(h->ev[i]);

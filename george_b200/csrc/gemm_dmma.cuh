@@ -1,0 +1,186 @@
+// gemm_dmma.cuh — batched FP64 GEMM on the tensor pipe (mma.sync.aligned.m8n8k4.f64 -> SASS DMMA.8x8x4).
+//
+// tcgen05 has no f64 kind, so the dense contractions of this solver (Cholesky trailing updates, HODLR Gram / update
+// products, triangular-solve updates) run on DMMA; measured issue-bound peak on B200: 37.2 TFLOP/s
+// (tools/fp64_peaks.cu, profiles/fp64_peaks_r01.txt; cuBLAS dgemm reaches 35.4).
+//
+//   C (M x N, column-major ldc)  op=  A' (M x K) * B' (K x N)
+//   A' element (m, k):  A_KCONTIG ? A[m*lda + k] : A[k*lda + m]      (i.e. A stored K x M   or   M x K, column-major)
+//   B' element (k, n):  B_KCONTIG ? B[n*ldb + k] : B[k*ldb + n]      (i.e. B stored K x N   or   N x K, column-major)
+//   op: GD_SUB  C -= A'B'   |  GD_ATOMIC_ADD  atomicAdd(C, A'B') (split-K)   |  lower: only entries with m >= n
+//
+// 128 x 128 x 16 CTA tile, 256 threads = 8 warps (2 x 4), 64 x 32 warp tile = 8 x 4 DMMA tiles, 3-stage cp.async
+// pipeline.  Shared-memory leading dimensions are = 4 (mod 16) doubles so that the (lane/4, lane%4) fragment pattern
+// of a half-warp touches 16 distinct 8-byte banks.
+#pragma once
+
+#include "common.cuh"
+
+namespace bgp {
+
+constexpr int GD_BM = 128, GD_BN = 128, GD_BK = 16, GD_THREADS = 256, GD_STAGES = 3;
+constexpr int GD_LDK = GD_BK + 4;    // [mn][k] layout
+constexpr int GD_LDM = GD_BM + 4;    // [k][mn] layout
+constexpr int GD_TILE_ELEMS = (GD_BM * GD_LDK > GD_BK * GD_LDM) ? GD_BM * GD_LDK : GD_BK * GD_LDM;  // 2560 doubles
+constexpr size_t GD_SMEM_BYTES = sizeof(double) * 2 * GD_STAGES * GD_TILE_ELEMS;                      // 122880
+
+enum { GD_SUB = 0, GD_ATOMIC_ADD = 1 };
+
+struct GemmDesc {
+  const double* A;
+  const double* B;
+  double* C;
+  int M, N, K, mode;   // mode: GD_SUB | GD_ATOMIC_ADD, bit 8: lower-triangular output only
+  int64_t lda, ldb, ldc;
+};
+constexpr int GD_LOWER = 256;
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid) {
+  const uint32_t s = smem_u32(smem);
+  const int sz = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// load one BK-slab of an operand tile (128 rows/cols x 16 k) into shared memory
+template <bool KCONTIG>
+__device__ __forceinline__ void gd_load_tile(double* sm, const double* __restrict__ G, int64_t ld, int mn0, int mn_max,
+                                             int k0, int k_max) {
+  if (KCONTIG) {
+    // global: element (mn, k) at G[mn*ld + k]; shared: sm[mn*GD_LDK + k]
+#pragma unroll
+    for (int i = 0; i < (GD_BM * GD_BK) / GD_THREADS; ++i) {
+      const int t = threadIdx.x + i * GD_THREADS;
+      const int k = t % GD_BK, mn = t / GD_BK;
+      const bool ok = (mn0 + mn < mn_max) && (k0 + k < k_max);
+      const double* src = ok ? (G + (int64_t)(mn0 + mn) * ld + k0 + k) : G;
+      cp_async8(sm + mn * GD_LDK + k, src, ok);
+    }
+  } else {
+    // global: element (mn, k) at G[k*ld + mn]; shared: sm[k*GD_LDM + mn]
+#pragma unroll
+    for (int i = 0; i < (GD_BM * GD_BK) / GD_THREADS; ++i) {
+      const int t = threadIdx.x + i * GD_THREADS;
+      const int mn = t % GD_BM, k = t / GD_BM;
+      const bool ok = (mn0 + mn < mn_max) && (k0 + k < k_max);
+      const double* src = ok ? (G + (int64_t)(k0 + k) * ld + mn0 + mn) : G;
+      cp_async8(sm + k * GD_LDM + mn, src, ok);
+    }
+  }
+}
+
+template <bool A_KCONTIG, bool B_KCONTIG>
+__global__ void __launch_bounds__(GD_THREADS) gemm_dmma_kernel(const GemmDesc* __restrict__ descs, const int* info) {
+  if (info && *info != 0) return;
+  const GemmDesc d = descs[blockIdx.z];
+  const int m0 = blockIdx.x * GD_BM, n0 = blockIdx.y * GD_BN;
+  if (m0 >= d.M || n0 >= d.N) return;
+  const bool lower = (d.mode & GD_LOWER) != 0;
+  if (lower && m0 + GD_BM <= n0) return;  // tile strictly above the diagonal
+  extern __shared__ __align__(16) double gd_smem[];
+  double* sA = gd_smem;
+  double* sB = gd_smem + GD_STAGES * GD_TILE_ELEMS;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
+  const int lr = lane >> 2, lc = lane & 3;
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+  const int nk = (d.K + GD_BK - 1) / GD_BK;
+  // prologue
+#pragma unroll
+  for (int s = 0; s < GD_STAGES - 1; ++s) {
+    if (s < nk) {
+      gd_load_tile<A_KCONTIG>(sA + s * GD_TILE_ELEMS, d.A, d.lda, m0, d.M, s * GD_BK, d.K);
+      gd_load_tile<B_KCONTIG>(sB + s * GD_TILE_ELEMS, d.B, d.ldb, n0, d.N, s * GD_BK, d.K);
+    }
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<GD_STAGES - 2>();
+    __syncthreads();
+    {
+      const int nxt = kt + GD_STAGES - 1;
+      if (nxt < nk) {
+        const int s = nxt % GD_STAGES;
+        gd_load_tile<A_KCONTIG>(sA + s * GD_TILE_ELEMS, d.A, d.lda, m0, d.M, nxt * GD_BK, d.K);
+        gd_load_tile<B_KCONTIG>(sB + s * GD_TILE_ELEMS, d.B, d.ldb, n0, d.N, nxt * GD_BK, d.K);
+      }
+      cp_async_commit();
+    }
+    const double* a_s = sA + (kt % GD_STAGES) * GD_TILE_ELEMS;
+    const double* b_s = sB + (kt % GD_STAGES) * GD_TILE_ELEMS;
+#pragma unroll
+    for (int kk = 0; kk < GD_BK / 4; ++kk) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = wm * 64 + i * 8 + lr, k = kk * 4 + lc;
+        af[i] = A_KCONTIG ? a_s[m * GD_LDK + k] : a_s[k * GD_LDM + m];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = wn * 32 + j * 8 + lr, k = kk * 4 + lc;
+        bf[j] = B_KCONTIG ? b_s[n * GD_LDK + k] : b_s[k * GD_LDM + n];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: thread holds C(m = .. + lr, n = .. + 2*lc + {0,1})
+  const int op = d.mode & 0xff;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + wm * 64 + i * 8 + lr;
+    if (m >= d.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int n = n0 + wn * 32 + j * 8 + 2 * lc + e;
+        if (n >= d.N) continue;
+        if (lower && m < n) continue;
+        double* c = d.C + (int64_t)n * d.ldc + m;
+        if (op == GD_SUB) *c -= acc[i][j][e];
+        else atomicAdd(c, acc[i][j][e]);
+      }
+    }
+  }
+}
+
+// host launcher: all descriptors of a batch share the grid; maxM / maxN bound the tile grid
+template <bool A_KCONTIG, bool B_KCONTIG>
+inline int gemm_dmma_launch(const GemmDesc* d_descs, int batch, int maxM, int maxN, const int* info, cudaStream_t s) {
+  if (batch <= 0 || maxM <= 0 || maxN <= 0) return BGP_OK;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gemm_dmma_kernel<A_KCONTIG, B_KCONTIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GD_SMEM_BYTES);
+    attr = true;
+  }
+  for (int b0 = 0; b0 < batch; b0 += 65535) {
+    const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    dim3 grid((maxM + GD_BM - 1) / GD_BM, (maxN + GD_BN - 1) / GD_BN, nb);
+    gemm_dmma_kernel<A_KCONTIG, B_KCONTIG><<<grid, GD_THREADS, GD_SMEM_BYTES, s>>>(d_descs + b0, info);
+    BGP_LAUNCH_CHECK();
+  }
+  return BGP_OK;
+}
+
+}  // namespace bgp

@@ -212,9 +212,42 @@ __device__ __forceinline__ double leaf_value(const DevLeaf& L, const double* x1,
   return v;
 }
 
+// Fast path for 1-D inputs whose leaves all depend on d = x1 - x2 only (stationary kernels with a scalar metric,
+// ExpSine2, Cosine, Constant): no axis indirection, no metric loops.  Same arithmetic, same order, as the general path.
+#define BGP_FLAG_FAST1D 1
+__device__ __forceinline__ double leaf_value_1d(const DevLeaf& L, double d) {
+  switch (L.kernel_type) {
+    case BGP_K_EXP_SQUARED: { const double r2 = d * d * L.mvec[0]; return exp(-0.5 * r2); }
+    case BGP_K_MATERN32: { const double r2 = d * d * L.mvec[0]; const double r = sqrt(3.0 * r2); return (1.0 + r) * exp(-r); }
+    case BGP_K_MATERN52: { const double r2 = d * d * L.mvec[0]; const double r = sqrt(5.0 * r2); return (1 + r + 5.0 * r2 / 3.0) * exp(-r); }
+    case BGP_K_EXP: { const double r2 = d * d * L.mvec[0]; return exp(-sqrt(r2)); }
+    case BGP_K_RATIONAL_QUADRATIC: { const double r2 = d * d * L.mvec[0]; return pow(1 + 0.5 * r2 / L.rp[0], -L.rp[0]); }
+    case BGP_K_EXP_SINE2: { const double s = sin(d * L.rp[0]); return exp(-L.p[0] * s * s); }
+    case BGP_K_COSINE: return cos(d * L.rp[0]);
+    case BGP_K_CONSTANT: return L.rp[0];
+  }
+  return 0.0;
+}
+__device__ __forceinline__ double kernel_value_1d(const DevProgram& P, double d) {
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0;
+  const int n = P.n_nodes;
+  for (int i = 0; i < n; ++i) {
+    const int c = P.code[i];
+    if (c >= 0) {
+      const double v = leaf_value_1d(P.leaf[c], d);
+      s7 = s6; s6 = s5; s5 = s4; s4 = s3; s3 = s2; s2 = s1; s1 = s0; s0 = v;
+    } else {
+      s0 = (c == -1) ? (s1 + s0) : (s1 * s0);
+      s1 = s2; s2 = s3; s3 = s4; s4 = s5; s5 = s6; s6 = s7;
+    }
+  }
+  return s0;
+}
+
 // k(x1, x2): postfix interpreter with a shift-register operand stack (no dynamically indexed local memory).
 // P lives in shared memory; x1/x2 point at `ndim` doubles (shared, global or local).
 __device__ __forceinline__ double kernel_value(const DevProgram& P, const double* x1, const double* x2) {
+  if (P.flags & BGP_FLAG_FAST1D) return kernel_value_1d(P, x1[0] - x2[0]);
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0;
   const int n = P.n_nodes;
   for (int i = 0; i < n; ++i) {
