@@ -171,6 +171,27 @@ int build_dev_program(const bgp_kernel_spec_t* s, DevProgram* P) {
     else fast = (kt == BGP_K_EXP_SINE2 || kt == BGP_K_COSINE || kt == BGP_K_CONSTANT);
   }
   P->flags = fast ? 1 : 0;
+  // program shape:  [S]  or  [Constant, S, *] / [S, Constant, *]  with S in {ExpSquared, Matern32, Matern52, Exp}
+  P->shape = BGP_SHAPE_GENERIC; P->sc = 1.0; P->sm = 1.0;
+  if (fast) {
+    auto shape_of = [](int kt) {
+      switch (kt) {
+        case BGP_K_EXP_SQUARED: return (int)BGP_SHAPE_EXPSQ;
+        case BGP_K_MATERN32: return (int)BGP_SHAPE_M32;
+        case BGP_K_MATERN52: return (int)BGP_SHAPE_M52;
+        case BGP_K_EXP: return (int)BGP_SHAPE_EXP;
+        default: return 0;
+      }
+    };
+    if (P->n_nodes == 1 && shape_of(P->leaf[0].kernel_type)) {
+      P->shape = shape_of(P->leaf[0].kernel_type); P->sm = P->leaf[0].mvec[0]; P->sc = 1.0;
+    } else if (P->n_nodes == 3 && P->code[2] == -2 && nl == 2) {
+      const DevLeaf& a = P->leaf[0];
+      const DevLeaf& b = P->leaf[1];
+      if (a.kernel_type == BGP_K_CONSTANT && shape_of(b.kernel_type)) { P->shape = shape_of(b.kernel_type); P->sc = a.rp[0]; P->sm = b.mvec[0]; }
+      else if (b.kernel_type == BGP_K_CONSTANT && shape_of(a.kernel_type)) { P->shape = shape_of(a.kernel_type); P->sc = b.rp[0]; P->sm = a.mvec[0]; }
+    }
+  }
   return BGP_OK;
 }
 

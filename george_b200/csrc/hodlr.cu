@@ -198,20 +198,27 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   a.cand = h->d_cand.p; a.cand_k = h->d_cand_k.p; a.cand_words = h->d_cand_words.p; a.epart = h->d_epart.p;
   a.cchunk_node = h->d_cchunk_node.p; a.rchunk_node = h->d_rchunk_node.p; a.vpart = h->d_vpart.p; a.upart = h->d_upart.p;
   a.capmax = capmax; a.n_active = h->d_nactive.p;
-  a2_init_kernel<<<nn, 256, 0, s>>>(a);
+  static bool a2_attr = false;
+  if (!a2_attr) {
+    cudaFuncSetAttribute(a2_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A2NodeSmem));
+    cudaFuncSetAttribute(a2_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A2NodeSmem));
+    cudaFuncSetAttribute(a2_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A2NodeSmem));
+    a2_attr = true;
+  }
+  a2_init_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), s>>>(a);
   BGP_LAUNCH_CHECK();
   int active = nn, iters = 0;
   while (active > 0) {
     for (int rep = 0; rep < 8; ++rep) {
       a2_eval_kernel<<<dim3(ncc, A2_GROUPS), A2_THREADS, 0, s>>>(a);
       BGP_LAUNCH_CHECK();
-      a2_decide_kernel<<<nn, 128, 0, s>>>(a);
+      a2_decide_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), s>>>(a);
       BGP_LAUNCH_CHECK();
       a2_vnorm_kernel<<<ncc, A2_THREADS, 0, s>>>(a);
       BGP_LAUNCH_CHECK();
       a2_ucol_kernel<<<nrc, A2_THREADS, 0, s>>>(a);
       BGP_LAUNCH_CHECK();
-      a2_finish_kernel<<<nn, 128, 0, s>>>(a);
+      a2_finish_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), s>>>(a);
       BGP_LAUNCH_CHECK();
       iters++;
     }

@@ -20,9 +20,10 @@ namespace bgp {
 constexpr int A2_CHUNK = 1024;    // rows / columns per work item
 constexpr int A2_THREADS = 256;
 constexpr int A2_EPT = A2_CHUNK / A2_THREADS;  // elements per thread
-constexpr int A2_CG = 8;          // candidates evaluated together (register blocking)
+constexpr int A2_CG = 4;          // candidates evaluated together (register blocking)
 constexpr int A2_GROUPS = 4;      // candidate groups (gridDim.y of the eval kernel)
 constexpr int A2_BMAX = 2048;     // max speculative candidates per iteration
+constexpr int A2_HASH = 4096;     // open-addressing slots of the swap-pop overlay (>= 2 * A2_BMAX)
 
 struct A2Node {  // static description
   int row0, n_rows, col0, n_cols;
@@ -48,28 +49,75 @@ struct A2EPart {
 
 enum { A2_SELECT = 0, A2_ACCEPT = 1, A2_DONE = 2 };
 
-// draw up to B candidate rows speculatively (thread 0).  cand[c] = row, cand_k[c] = position drawn, words[c] = mt19937
-// words consumed up to and including draw c.  The index list is modified (swap-pop) and undone later if needed.
-__device__ inline void a2_generate(A2State& st, MT19937& spec, int* index, int* cand, int* cand_k, int* words, int bmax) {
-  const int B = min(min(st.B, bmax), st.n_index);
-  int w = 0;
-  int n_index = st.n_index;
-  for (int c = 0; c < B; ++c) {
-    const int k = mt_uniform(spec, (uint32_t)n_index, &w);
-    cand[c] = index[k];
-    cand_k[c] = k;
-    words[c] = w;
-    index[k] = index[n_index - 1];
-    n_index--;
-  }
-  st.ncand = B;
-}
-
 // cooperative 625-word copy of an mt19937 state (all threads of the CTA; caller synchronises)
 __device__ __forceinline__ void mt_copy(MT19937* dst, const MT19937* src) {
   const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
   uint32_t* d = reinterpret_cast<uint32_t*>(dst);
   for (int i = threadIdx.x; i < (int)(sizeof(MT19937) / 4); i += blockDim.x) d[i] = s[i];
+}
+
+// shared-memory workspace of the per-node kernels (dynamic shared memory)
+struct A2NodeSmem {
+  MT19937 rng;
+  int k[A2_BMAX];       // drawn positions
+  int ok[A2_BMAX];      // index[k_c] before this batch
+  int ol[A2_BMAX];      // index[n_index-1-c] before this batch
+  int hkey[A2_HASH];    // overlay: position -> value after the swap-pops so far
+  int hval[A2_HASH];
+  double red[32];
+  int redi[32];
+};
+
+__device__ __forceinline__ int a2_hash_find(const int* hkey, int pos) {
+  unsigned h = ((unsigned)pos * 2654435761u) & (A2_HASH - 1);
+  while (hkey[h] != -1 && hkey[h] != pos) h = (h + 1) & (A2_HASH - 1);
+  return (int)h;
+}
+
+// Draw the next min(B, bmax, n_index) candidate rows speculatively: k_c = uniform(0, n_index-1-c) from `S.rng`
+// (advanced), swap-pop on the index list (hodlr.h:179-183).  The positions depend on the RNG only, so the list
+// entries they touch are prefetched by the whole CTA and the dependent swap-pop chain runs in shared memory.
+// cand[c] = row, cand_k[c] = position, words[c] = mt19937 words consumed up to and including draw c.
+__device__ inline void a2_generate(A2State& st, A2NodeSmem& S, int* __restrict__ index, int* __restrict__ cand,
+                                   int* __restrict__ cand_k, int* __restrict__ words, int bmax) {
+  const int n_index = st.n_index;
+  const int B = min(min(st.B, bmax), n_index);
+  if (threadIdx.x == 0) {
+    int w = 0;
+    for (int c = 0; c < B; ++c) {
+      S.k[c] = mt_uniform(S.rng, (uint32_t)(n_index - c), &w);
+      words[c] = w;
+    }
+    st.ncand = B;
+  }
+  for (int t = threadIdx.x; t < A2_HASH; t += blockDim.x) S.hkey[t] = -1;
+  __syncthreads();
+  for (int c = threadIdx.x; c < B; c += blockDim.x) {
+    S.ok[c] = index[S.k[c]];
+    S.ol[c] = index[n_index - 1 - c];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < B; ++c) {
+      const int pos = S.k[c], last = n_index - 1 - c;
+      int h = a2_hash_find(S.hkey, pos);
+      const int val = (S.hkey[h] == pos) ? S.hval[h] : S.ok[c];
+      S.ok[c] = val;  // becomes cand[c]
+      const int hl = a2_hash_find(S.hkey, last);
+      const int lastval = (S.hkey[hl] == last) ? S.hval[hl] : S.ol[c];
+      h = a2_hash_find(S.hkey, pos);
+      S.hkey[h] = pos;
+      S.hval[h] = lastval;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < B; c += blockDim.x) {
+    cand[c] = S.ok[c];
+    cand_k[c] = S.k[c];
+    const int h = a2_hash_find(S.hkey, S.k[c]);
+    index[S.k[c]] = S.hval[h];  // final content of every touched position (duplicates write the same value)
+  }
+  __syncthreads();
 }
 
 struct A2Args {
@@ -99,45 +147,35 @@ struct A2Args {
 };
 
 // ---- init: index list, RNG seed, first candidates -------------------------------------------------------------
-__global__ void __launch_bounds__(256) a2_init_kernel(A2Args a) {
-  __shared__ MT19937 rng;
+__global__ void __launch_bounds__(A2_THREADS) a2_init_kernel(A2Args a) {
+  extern __shared__ __align__(16) unsigned char a2_smem_raw[];
+  A2NodeSmem& S = *reinterpret_cast<A2NodeSmem*>(a2_smem_raw);
   const int nid = blockIdx.x;
   const A2Node nd = a.nodes[nid];
   A2State& st = a.states[nid];
   int* index = a.idx_ws + nd.idx_off;
   for (int n = threadIdx.x; n < nd.n_rows; n += blockDim.x) index[n] = n;
-  __syncthreads();
   if (threadIdx.x == 0) {
-    mt_seed(rng, node_seed(a.seed, nd.pre_id));
+    mt_seed(S.rng, node_seed(a.seed, nd.pre_id));
     st.rank = 0; st.draws = 0; st.n_index = nd.n_rows; st.fallback = 0; st.status = 0; st.active = 1;
-    st.phase = A2_SELECT; st.B = 4; st.norm = 0.0; st.pivot = 0.0; st.piv_i = 0; st.piv_j = 0;
+    st.phase = A2_SELECT; st.B = 4; st.norm = 0.0; st.pivot = 0.0; st.piv_i = 0; st.piv_j = 0; st.ncand = 0;
   }
   __syncthreads();
-  mt_copy(&st.rng, &rng);  // committed = state before the speculative draws
+  mt_copy(&st.rng, &S.rng);  // committed = state before the speculative draws
   __syncthreads();
-  if (threadIdx.x == 0) {
-    if (nd.cap <= 0) { st.status = 1; st.phase = A2_DONE; st.active = 0; atomicSub(a.n_active, 1); }
-    else a2_generate(st, rng, index, a.cand + nd.cand_off, a.cand_k + nd.cand_off, a.cand_words + nd.cand_off, nd.bmax);
+  if (nd.cap <= 0) {
+    if (threadIdx.x == 0) { st.status = 1; st.phase = A2_DONE; st.active = 0; atomicSub(a.n_active, 1); }
+    return;
   }
+  a2_generate(st, S, index, a.cand + nd.cand_off, a.cand_k + nd.cand_off, a.cand_words + nd.cand_off, nd.bmax);
 }
 
 // ---- eval: residual maxima of the pending candidate rows ------------------------------------------------------
-__global__ void __launch_bounds__(A2_THREADS) a2_eval_kernel(A2Args a) {
-  __shared__ DevProgram P;
-  __shared__ double s_x[A2_CG][ACA_MAX_NDIM];
-  __shared__ double s_u[A2_CG][128 + 1];  // U(i, k) for a k-tile of 128
-  __shared__ double s_red[A2_CG][A2_THREADS / 32];
-  __shared__ int s_redi[A2_CG][A2_THREADS / 32];
+template <class KFn>
+__device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, int rank, int ncand, int ndim, KFn fn,
+                                             double (*s_x)[ACA_MAX_NDIM], double (*s_u)[128 + 1],
+                                             double (*s_red)[A2_THREADS / 32], int (*s_redi)[A2_THREADS / 32]) {
   const int chunk = blockIdx.x;
-  const int nid = a.cchunk_node[chunk];
-  const A2State& st = a.states[nid];
-  if (st.phase != A2_SELECT || !st.active) return;
-  const int ncand = st.ncand;
-  if (ncand <= (int)blockIdx.y * A2_CG) return;
-  const A2Node nd = a.nodes[nid];
-  stage_program(&P, a.prog);
-  const int ndim = a.prog->ndim;
-  const int rank = st.rank;
   const int lc = chunk - nd.cchunk0;
   const int c_lo = lc * A2_CHUNK;
   const int c_n = min(A2_CHUNK, nd.n_cols - c_lo);
@@ -147,7 +185,6 @@ __global__ void __launch_bounds__(A2_THREADS) a2_eval_kernel(A2Args a) {
   const int* cand = a.cand + nd.cand_off;
   A2EPart* ep = a.epart + nd.epart_off;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();
 
   for (int cb = blockIdx.y * A2_CG; cb < ncand; cb += A2_GROUPS * A2_CG) {
     const int ncb = min(A2_CG, ncand - cb);
@@ -155,26 +192,22 @@ __global__ void __launch_bounds__(A2_THREADS) a2_eval_kernel(A2Args a) {
     __syncthreads();
     for (int t = threadIdx.x; t < A2_CG * ndim; t += A2_THREADS) {
       const int c = t / ndim, q = t % ndim;
-      s_x[c][q] = (c < ncb) ? xr[(int64_t)cand[cb + c] * ndim + q] : 0.0;
+      s_x[c][q] = xr[(int64_t)cand[cb + min(c, ncb - 1)] * ndim + q];  // pad with a repeat of the last candidate
     }
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < A2_EPT; ++e) {
       const int n = threadIdx.x + e * A2_THREADS;
-      if (n < c_n) {
+      const double* x2 = xc + (int64_t)min(n, c_n - 1) * ndim;
 #pragma unroll
-        for (int c = 0; c < A2_CG; ++c) vals[c][e] = (c < ncb) ? kernel_value(P, s_x[c], xc + (int64_t)n * ndim) : 0.0;
-      } else {
-#pragma unroll
-        for (int c = 0; c < A2_CG; ++c) vals[c][e] = 0.0;
-      }
+      for (int c = 0; c < A2_CG; ++c) vals[c][e] = fn(s_x[c], x2);
     }
     for (int k0 = 0; k0 < rank; k0 += 128) {
       const int nk = min(128, rank - k0);
       __syncthreads();
       for (int t = threadIdx.x; t < A2_CG * nk; t += A2_THREADS) {
         const int c = t / nk, k = t % nk;
-        s_u[c][k] = (c < ncb) ? __ldcg(Vcols + (int64_t)(k0 + k) * a.ld + nd.row0 + cand[cb + c]) : 0.0;
+        s_u[c][k] = __ldcg(Vcols + (int64_t)(k0 + k) * a.ld + nd.row0 + cand[cb + min(c, ncb - 1)]);
       }
       __syncthreads();
       for (int k = 0; k < nk; ++k) {
@@ -182,7 +215,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_eval_kernel(A2Args a) {
 #pragma unroll
         for (int e = 0; e < A2_EPT; ++e) {
           const int n = threadIdx.x + e * A2_THREADS;
-          vk[e] = (n < c_n) ? Vcols[(int64_t)(k0 + k) * a.ld + nd.col0 + c_lo + n] : 0.0;
+          vk[e] = Vcols[(int64_t)(k0 + k) * a.ld + nd.col0 + c_lo + min(n, c_n - 1)];
         }
 #pragma unroll
         for (int c = 0; c < A2_CG; ++c) {
@@ -192,7 +225,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_eval_kernel(A2Args a) {
         }
       }
     }
-    // per-candidate arg-max over the chunk
+    // per-candidate arg-max over the chunk (lowest column on ties)
 #pragma unroll
     for (int c = 0; c < A2_CG; ++c) {
       double best = -1.0, bval = 0.0;
@@ -203,7 +236,6 @@ __global__ void __launch_bounds__(A2_THREADS) a2_eval_kernel(A2Args a) {
         const double av = fabs(vals[c][e]);
         if (n < c_n && av > best) { best = av; bidx = c_lo + n; bval = vals[c][e]; }
       }
-      // warp arg-max carrying the signed value
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const double ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -230,12 +262,32 @@ __global__ void __launch_bounds__(A2_THREADS) a2_eval_kernel(A2Args a) {
   }
 }
 
+__global__ void __launch_bounds__(A2_THREADS, 2) a2_eval_kernel(A2Args a) {
+  __shared__ DevProgram P;
+  __shared__ double s_x[A2_CG][ACA_MAX_NDIM];
+  __shared__ double s_u[A2_CG][128 + 1];  // U(i, k) for a k-tile of 128
+  __shared__ double s_red[A2_CG][A2_THREADS / 32];
+  __shared__ int s_redi[A2_CG][A2_THREADS / 32];
+  const int nid = a.cchunk_node[blockIdx.x];
+  const A2State& st = a.states[nid];
+  if (st.phase != A2_SELECT || !st.active) return;
+  const int ncand = st.ncand;
+  if (ncand <= (int)blockIdx.y * A2_CG) return;
+  const A2Node nd = a.nodes[nid];
+  stage_program(&P, a.prog);
+  const int rank = st.rank;
+  __syncthreads();
+  const int ndim = P.ndim;
+  BGP_DISPATCH_SHAPE(P, a2_eval_body(a, nd, rank, ncand, ndim, fn, s_x, s_u, s_red, s_redi));
+}
+
 // ---- decide: first usable candidate wins; commit the RNG / index list up to it ----------------------------------
-__global__ void __launch_bounds__(128) a2_decide_kernel(A2Args a) {
-  __shared__ MT19937 rng;
+__global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
+  extern __shared__ __align__(16) unsigned char a2_smem_raw[];
+  A2NodeSmem& S = *reinterpret_cast<A2NodeSmem*>(a2_smem_raw);
   __shared__ int s_winner;
-  __shared__ double s_val[128];
-  __shared__ int s_idx[128];
+  __shared__ double s_val[64];
+  __shared__ int s_idx[64];
   const int nid = blockIdx.x;
   A2State& st = a.states[nid];
   if (st.phase != A2_SELECT || !st.active) return;
@@ -246,60 +298,73 @@ __global__ void __launch_bounds__(128) a2_decide_kernel(A2Args a) {
   int* cand_k = a.cand_k + nd.cand_off;
   int* words = a.cand_words + nd.cand_off;
   int* index = a.idx_ws + nd.idx_off;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_winner = 0x7fffffff;
   __syncthreads();
-  // candidates in blocks of 128, in order; stop at the first block containing a winner
-  for (int c0 = 0; c0 < ncand; c0 += 128) {
-    const int c = c0 + threadIdx.x;
-    double bval = 0.0;
-    int bidx = 0x7fffffff;
-    if (c < ncand) {
-      for (int ch = 0; ch < nd.n_cchunks; ++ch) {
+  // candidates in blocks of 64 (8 per warp), in sequence order; lanes sweep the chunks (coalesced)
+  for (int c0 = 0; c0 < ncand; c0 += 64) {
+    for (int q = 0; q < 8; ++q) {
+      const int c = c0 + warp * 8 + q;
+      if (c >= ncand) break;
+      double bval = 0.0;
+      int bidx = 0x7fffffff;
+      for (int ch = lane; ch < nd.n_cchunks; ch += 32) {
         const A2EPart p = ep[(int64_t)c * nd.n_cchunks + ch];
         if (fabs(p.val) > fabs(bval) || (fabs(p.val) == fabs(bval) && p.idx < bidx)) { bval = p.val; bidx = p.idx; }
       }
-      if (!(fabs(bval) < 1e-14)) atomicMin(&s_winner, c);  // hodlr.h:191 (NaN also leaves the loop, as in the reference)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bval, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (fabs(ov) > fabs(bval) || (fabs(ov) == fabs(bval) && oi < bidx)) { bval = ov; bidx = oi; }
+      }
+      if (lane == 0) {
+        s_val[c - c0] = bval;
+        s_idx[c - c0] = bidx;
+        if (!(fabs(bval) < 1e-14)) atomicMin(&s_winner, c);  // hodlr.h:191 (a NaN also leaves the loop, as there)
+      }
     }
-    s_val[threadIdx.x] = bval;
-    s_idx[threadIdx.x] = bidx;
     __syncthreads();
     if (s_winner != 0x7fffffff) break;
     __syncthreads();
   }
   const int p = s_winner;
   // commit the stream: replay exactly the words consumed up to the winner (or the whole batch)
-  mt_copy(&rng, &st.rng);
+  mt_copy(&S.rng, &st.rng);
   __syncthreads();
   if (threadIdx.x == 0) {
     const int w = (p != 0x7fffffff) ? words[p] : (ncand > 0 ? words[ncand - 1] : 0);
-    for (int q = 0; q < w; ++q) (void)mt_next(rng);
+    for (int q = 0; q < w; ++q) (void)mt_next(S.rng);
     st.draws += w;
   }
   __syncthreads();
-  mt_copy(&st.rng, &rng);
+  mt_copy(&st.rng, &S.rng);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    if (p != 0x7fffffff) {
+  if (p != 0x7fffffff) {
+    if (threadIdx.x == 0) {
       // undo the speculative swap-pops beyond the winner, newest first
       for (int c = ncand - 1; c > p; --c) index[cand_k[c]] = cand[c];
       st.n_index -= (p + 1);
       st.piv_i = cand[p];
-      st.piv_j = s_idx[p & 127];
-      st.pivot = s_val[p & 127];
+      st.piv_j = s_idx[p & 63];
+      st.pivot = s_val[p & 63];
       st.phase = A2_ACCEPT;
       st.B = max(1, min(st.B, 2 * (p + 1)));
-    } else {
-      st.n_index -= ncand;
-      st.B = min(2 * st.B, A2_BMAX);
-      if (st.n_index == 0) {
-        st.fallback = 1;  // rows exhausted (hodlr.h:161); dense fill (if requested) happens after the loop
-        st.phase = A2_DONE; st.active = 0;
-        atomicSub(a.n_active, 1);
-      } else {
-        a2_generate(st, rng, index, cand, cand_k, words, nd.bmax);
-      }
+    }
+    return;
+  }
+  if (threadIdx.x == 0) {
+    st.n_index -= ncand;
+    st.B = min(4 * st.B, A2_BMAX);
+    if (st.n_index == 0) {
+      st.fallback = 1;  // rows exhausted (hodlr.h:161); dense fill (if requested) happens after the loop
+      st.phase = A2_DONE; st.active = 0;
+      atomicSub(a.n_active, 1);
     }
   }
+  __syncthreads();
+  if (st.n_index == 0) return;
+  a2_generate(st, S, index, cand, cand_k, words, nd.bmax);
 }
 
 // ---- vnorm: normalised row residual -> panel column `rank`, partial ||v||^2 and V_prev^T v ----------------------
@@ -438,9 +503,10 @@ __global__ void __launch_bounds__(A2_THREADS) a2_ucol_kernel(A2Args a) {
 }
 
 // ---- finish: stopping rule (hodlr.h:202-214), next candidates -----------------------------------------------------
-__global__ void __launch_bounds__(128) a2_finish_kernel(A2Args a) {
-  __shared__ MT19937 rng;
-  __shared__ double red[32];
+__global__ void __launch_bounds__(A2_THREADS) a2_finish_kernel(A2Args a) {
+  extern __shared__ __align__(16) unsigned char a2_smem_raw[];
+  A2NodeSmem& S = *reinterpret_cast<A2NodeSmem*>(a2_smem_raw);
+  __shared__ int s_done;
   const int nid = blockIdx.x;
   A2State& st = a.states[nid];
   if (st.phase != A2_ACCEPT || !st.active) return;
@@ -449,8 +515,8 @@ __global__ void __launch_bounds__(128) a2_finish_kernel(A2Args a) {
   double vn2 = 0.0, un2 = 0.0;
   for (int c = threadIdx.x; c < nd.n_cchunks; c += blockDim.x) vn2 += a.vpart[(int64_t)(nd.cchunk0 + c) * (a.capmax + 1)];
   for (int c = threadIdx.x; c < nd.n_rchunks; c += blockDim.x) un2 += a.upart[(int64_t)(nd.rchunk0 + c) * (a.capmax + 1)];
-  vn2 = block_sum(vn2, red);
-  un2 = block_sum(un2, red);
+  vn2 = block_sum(vn2, S.red);
+  un2 = block_sum(un2, S.red);
   double vdot = 0.0, udot = 0.0;
   for (int k = threadIdx.x; k < rank; k += blockDim.x) {
     double sv = 0.0, su = 0.0;
@@ -459,10 +525,9 @@ __global__ void __launch_bounds__(128) a2_finish_kernel(A2Args a) {
     vdot = fmax(vdot, fabs(sv));
     udot = fmax(udot, fabs(su));
   }
-  vdot = block_max(vdot, red);
-  udot = block_max(udot, red);
-  mt_copy(&rng, &st.rng);
-  __syncthreads();
+  vdot = block_max(vdot, S.red);
+  udot = block_max(udot, S.red);
+  mt_copy(&S.rng, &st.rng);
   if (threadIdx.x == 0) {
     a.piv_rows[nd.piv_off + rank] = st.piv_i;
     a.piv_cols[nd.piv_off + rank] = st.piv_j;
@@ -486,10 +551,12 @@ __global__ void __launch_bounds__(128) a2_finish_kernel(A2Args a) {
       atomicSub(a.n_active, 1);
     } else {
       st.phase = A2_SELECT;
-      a2_generate(st, rng, a.idx_ws + nd.idx_off, a.cand + nd.cand_off, a.cand_k + nd.cand_off, a.cand_words + nd.cand_off,
-                  nd.bmax);
     }
+    s_done = done ? 1 : 0;
   }
+  __syncthreads();
+  if (s_done) return;
+  a2_generate(st, S, a.idx_ws + nd.idx_off, a.cand + nd.cand_off, a.cand_k + nd.cand_off, a.cand_words + nd.cand_off, nd.bmax);
 }
 
 // ---- dense fallback fill (hodlr.h:161-176): V = I, U = K(rows, cols) ---------------------------------------------

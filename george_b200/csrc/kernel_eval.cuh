@@ -26,8 +26,10 @@ struct DevLeaf {
 
 struct DevProgram {
   int n_nodes, ndim, n_params_total, n_leaves;
-  int flags;  // bit0: every leaf is a stationary isotropic/axis-aligned or 1-axis kernel (fast path hint)
-  int _pad[3];
+  int flags;  // bit0: 1-D input and every leaf depends on d = x1 - x2 only (fast path)
+  int shape;  // 0 generic; otherwise BGP_SHAPE_*: the whole program is  sc * f(d*d*sm)  with f a stationary profile
+  int _pad[2];
+  double sc, sm;
   signed char code[BGP_MAX_NODES];  // >=0: leaf index, -1: sum, -2: product
   DevLeaf leaf[BGP_MAX_LEAVES];
 };
@@ -215,6 +217,24 @@ __device__ __forceinline__ double leaf_value(const DevLeaf& L, const double* x1,
 // Fast path for 1-D inputs whose leaves all depend on d = x1 - x2 only (stationary kernels with a scalar metric,
 // ExpSine2, Cosine, Constant): no axis indirection, no metric loops.  Same arithmetic, same order, as the general path.
 #define BGP_FLAG_FAST1D 1
+enum { BGP_SHAPE_GENERIC = 0, BGP_SHAPE_EXPSQ = 1, BGP_SHAPE_M32 = 2, BGP_SHAPE_M52 = 3, BGP_SHAPE_EXP = 4 };
+
+// compile-time specialised evaluators for the commonest programs ("c * StationaryKernel(metric)" on 1-D inputs):
+// the interpreter disappears and independent evaluations can be interleaved by the compiler.
+template <int SHAPE>
+struct ScaledProfile1D {
+  double c, m;
+  __device__ __forceinline__ double operator()(const double* x1, const double* x2) const {
+    const double d = x1[0] - x2[0];
+    const double r2 = d * d * m;
+    double f;
+    if (SHAPE == BGP_SHAPE_EXPSQ) f = exp(-0.5 * r2);
+    else if (SHAPE == BGP_SHAPE_M32) { const double r = sqrt(3.0 * r2); f = (1.0 + r) * exp(-r); }
+    else if (SHAPE == BGP_SHAPE_M52) { const double r = sqrt(5.0 * r2); f = (1 + r + 5.0 * r2 / 3.0) * exp(-r); }
+    else f = exp(-sqrt(r2));
+    return c * f;
+  }
+};
 __device__ __forceinline__ double leaf_value_1d(const DevLeaf& L, double d) {
   switch (L.kernel_type) {
     case BGP_K_EXP_SQUARED: { const double r2 = d * d * L.mvec[0]; return exp(-0.5 * r2); }
@@ -262,6 +282,20 @@ __device__ __forceinline__ double kernel_value(const DevProgram& P, const double
   }
   return s0;
 }
+
+struct GenericKernelFn {
+  const DevProgram* P;
+  __device__ __forceinline__ double operator()(const double* x1, const double* x2) const { return kernel_value(*P, x1, x2); }
+};
+// run `body(fn)` with the evaluator specialised for the program's shape
+#define BGP_DISPATCH_SHAPE(P, BODY)                                                                   \
+  switch ((P).shape) {                                                                                \
+    case BGP_SHAPE_EXPSQ: { ScaledProfile1D<BGP_SHAPE_EXPSQ> fn{(P).sc, (P).sm}; BODY; } break;       \
+    case BGP_SHAPE_M32: { ScaledProfile1D<BGP_SHAPE_M32> fn{(P).sc, (P).sm}; BODY; } break;           \
+    case BGP_SHAPE_M52: { ScaledProfile1D<BGP_SHAPE_M52> fn{(P).sc, (P).sm}; BODY; } break;           \
+    case BGP_SHAPE_EXP: { ScaledProfile1D<BGP_SHAPE_EXP> fn{(P).sc, (P).sm}; BODY; } break;           \
+    default: { GenericKernelFn fn{&(P)}; BODY; } break;                                               \
+  }
 
 // value + hyper-parameter gradient (kernels.h:81-94 Sum, 117-139 Product, per-leaf gradient() methods).
 // grad has n_params_total entries; entries with which[i]==0 are 0.  Not on the log-likelihood hot path.
