@@ -68,6 +68,7 @@ struct bgp_hodlr {
   DevBuf<A2State> d_a2states;
   DevBuf<A2EPart> d_epart;
   DevBuf<int> d_cand, d_cand_k, d_cand_words, d_cchunk_node, d_rchunk_node, d_nactive;
+  DevBuf<unsigned long long> d_cmax;
   DevBuf<double> d_vpart, d_upart;
   int aca_iters = 0;
   size_t w_cap = 0;
@@ -181,6 +182,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   BGP_TRY(h->d_cand.reserve((size_t)cand_total, s));
   BGP_TRY(h->d_cand_k.reserve((size_t)cand_total, s));
   BGP_TRY(h->d_cand_words.reserve((size_t)cand_total, s));
+  BGP_TRY(h->d_cmax.reserve((size_t)cand_total, s));
   BGP_TRY(h->d_epart.reserve((size_t)epart_total, s));
   BGP_TRY(h->d_cchunk_node.reserve(ncc, s));
   BGP_TRY(h->d_rchunk_node.reserve(nrc, s));
@@ -195,7 +197,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   a.prog = h->d_prog.p; a.x = h->d_x.p; a.nodes = h->d_a2nodes.p; a.states = h->d_a2states.p; a.n_nodes = nn;
   a.Vp = h->d_V.p; a.ld = h->n; a.tol = h->opts.tol; a.seed = (uint32_t)h->opts.seed; a.exhaust_mode = h->opts.exhaust_mode;
   a.idx_ws = h->d_idx.p; a.piv_rows = h->d_piv_rows.p; a.piv_cols = h->d_piv_cols.p;
-  a.cand = h->d_cand.p; a.cand_k = h->d_cand_k.p; a.cand_words = h->d_cand_words.p; a.epart = h->d_epart.p;
+  a.cand = h->d_cand.p; a.cand_k = h->d_cand_k.p; a.cand_words = h->d_cand_words.p; a.cmax = h->d_cmax.p; a.epart = h->d_epart.p;
   a.cchunk_node = h->d_cchunk_node.p; a.rchunk_node = h->d_rchunk_node.p; a.vpart = h->d_vpart.p; a.upart = h->d_upart.p;
   a.capmax = capmax; a.n_active = h->d_nactive.p;
   static bool a2_attr = false;
@@ -582,7 +584,7 @@ void bgp_hodlr_destroy(bgp_hodlr_t* h) {
   h->d_ticket.release(); h->d_chain_done.release(); h->d_ncols_by_depth.release(); h->d_chain_state.release();
   h->d_a2nodes.release(); h->d_a2states.release(); h->d_epart.release(); h->d_cand.release(); h->d_cand_k.release();
   h->d_cand_words.release(); h->d_cchunk_node.release(); h->d_rchunk_node.release(); h->d_nactive.release();
-  h->d_vpart.release(); h->d_upart.release();
+  h->d_vpart.release(); h->d_upart.release(); h->d_cmax.release();
   if (h->sA) {
     cudaStreamSynchronize(h->sA); cudaStreamSynchronize(h->sB);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);

@@ -56,6 +56,57 @@ __device__ __forceinline__ void mt_copy(MT19937* dst, const MT19937* src) {
   for (int i = threadIdx.x; i < (int)(sizeof(MT19937) / 4); i += blockDim.x) d[i] = s[i];
 }
 
+// cooperative twist of the whole state (3 dependent phases of <= 227 independent elements + the last word)
+__device__ __forceinline__ void mt_twist_coop(MT19937& g) {
+  auto step = [&](int i, uint32_t a, uint32_t b, uint32_t m) {
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    g.mt[i] = m ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+  };
+  for (int i = threadIdx.x; i < 227; i += blockDim.x) step(i, g.mt[i], g.mt[i + 1], g.mt[i + 397]);
+  __syncthreads();
+  for (int i = 227 + threadIdx.x; i < 454; i += blockDim.x) step(i, g.mt[i], g.mt[i + 1], g.mt[i - 227]);
+  __syncthreads();
+  for (int i = 454 + threadIdx.x; i < 623; i += blockDim.x) step(i, g.mt[i], g.mt[i + 1], g.mt[i - 227]);
+  __syncthreads();
+  if (threadIdx.x == 0) { step(623, g.mt[623], g.mt[0], g.mt[396]); g.idx = 0; }
+  __syncthreads();
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+  y ^= (y >> 11);
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= (y >> 18);
+  return y;
+}
+// the next `n` tempered words of the stream into out[] (state advanced); all threads of the CTA
+__device__ inline void mt_fill_coop(MT19937& g, uint32_t* out, int n) {
+  int done = 0;
+  __syncthreads();
+  while (done < n) {
+    if (g.idx >= 624) mt_twist_coop(g);
+    const int idx = g.idx;
+    const int take = min(n - done, 624 - idx);
+    for (int t = threadIdx.x; t < take; t += blockDim.x) out[done + t] = mt_temper(g.mt[idx + t]);
+    __syncthreads();
+    if (threadIdx.x == 0) g.idx = idx + take;
+    __syncthreads();
+    done += take;
+  }
+}
+// skip `n` words of the stream (state advanced); all threads of the CTA
+__device__ inline void mt_skip_coop(MT19937& g, int n) {
+  __syncthreads();
+  while (n > 0) {
+    if (g.idx >= 624) mt_twist_coop(g);
+    const int idx = g.idx;
+    const int take = min(n, 624 - idx);
+    __syncthreads();
+    if (threadIdx.x == 0) g.idx = idx + take;
+    __syncthreads();
+    n -= take;
+  }
+}
+
 // shared-memory workspace of the per-node kernels (dynamic shared memory)
 struct A2NodeSmem {
   MT19937 rng;
@@ -64,8 +115,10 @@ struct A2NodeSmem {
   int ol[A2_BMAX];      // index[n_index-1-c] before this batch
   int hkey[A2_HASH];    // overlay: position -> value after the swap-pops so far
   int hval[A2_HASH];
+  uint32_t raw[A2_BMAX]; // raw mt19937 words of the batch
   double red[32];
   int redi[32];
+  int flag;
 };
 
 __device__ __forceinline__ int a2_hash_find(const int* hkey, int pos) {
@@ -79,19 +132,42 @@ __device__ __forceinline__ int a2_hash_find(const int* hkey, int pos) {
 // entries they touch are prefetched by the whole CTA and the dependent swap-pop chain runs in shared memory.
 // cand[c] = row, cand_k[c] = position, words[c] = mt19937 words consumed up to and including draw c.
 __device__ inline void a2_generate(A2State& st, A2NodeSmem& S, int* __restrict__ index, int* __restrict__ cand,
-                                   int* __restrict__ cand_k, int* __restrict__ words, int bmax) {
+                                   int* __restrict__ cand_k, int* __restrict__ words, int bmax,
+                                   unsigned long long* __restrict__ cmax) {
   const int n_index = st.n_index;
   const int B = min(min(st.B, bmax), n_index);
-  if (threadIdx.x == 0) {
-    int w = 0;
-    for (int c = 0; c < B; ++c) {
-      S.k[c] = mt_uniform(S.rng, (uint32_t)(n_index - c), &w);
-      words[c] = w;
-    }
-    st.ncand = B;
+  // Lemire's multiply-shift rejects with probability s / 2^32 per draw; draw B words in parallel assuming none does and
+  // fall back to the one-word-at-a-time loop (from a saved state) in the rare batch where a rejection shows up.
+  if (threadIdx.x == 0) { S.flag = 0; st.ncand = B; }
+  const int idx0 = S.rng.idx;
+  mt_fill_coop(S.rng, S.raw, B);
+  for (int c = threadIdx.x; c < B; c += blockDim.x) {
+    const uint32_t srange = (uint32_t)(n_index - c);
+    const uint64_t prod = (uint64_t)S.raw[c] * (uint64_t)srange;
+    const uint32_t low = (uint32_t)prod;
+    if (low < srange && low < (0u - srange) % srange) S.flag = 1;
+    S.k[c] = (int)(prod >> 32);
+    words[c] = c + 1;
+    cmax[c] = 0ull;
   }
   for (int t = threadIdx.x; t < A2_HASH; t += blockDim.x) S.hkey[t] = -1;
   __syncthreads();
+  if (S.flag) {
+    // exact replay: the batch consumed B words so far; rewind by re-deriving the state is not possible in place, so
+    // the caller-visible committed state (st.rng) is the restart point.
+    __syncthreads();
+    mt_copy(&S.rng, &st.rng);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int w = 0;
+      for (int c = 0; c < B; ++c) {
+        S.k[c] = mt_uniform(S.rng, (uint32_t)(n_index - c), &w);
+        words[c] = w;
+      }
+    }
+    __syncthreads();
+  }
+  (void)idx0;
   for (int c = threadIdx.x; c < B; c += blockDim.x) {
     S.ok[c] = index[S.k[c]];
     S.ol[c] = index[n_index - 1 - c];
@@ -137,6 +213,7 @@ struct A2Args {
   int* cand;       // candidate rows          [cand_off + c]
   int* cand_k;     // drawn positions
   int* cand_words; // cumulative words
+  unsigned long long* cmax;  // per candidate: bit pattern of max |residual| over all chunks (atomicMax)
   A2EPart* epart;  // [epart_off + c * n_cchunks + chunk]
   const int* cchunk_node;  // chunk -> node
   const int* rchunk_node;
@@ -167,7 +244,8 @@ __global__ void __launch_bounds__(A2_THREADS) a2_init_kernel(A2Args a) {
     if (threadIdx.x == 0) { st.status = 1; st.phase = A2_DONE; st.active = 0; atomicSub(a.n_active, 1); }
     return;
   }
-  a2_generate(st, S, index, a.cand + nd.cand_off, a.cand_k + nd.cand_off, a.cand_words + nd.cand_off, nd.bmax);
+  a2_generate(st, S, index, a.cand + nd.cand_off, a.cand_k + nd.cand_off, a.cand_words + nd.cand_off, nd.bmax,
+              a.cmax + nd.cand_off);
 }
 
 // ---- eval: residual maxima of the pending candidate rows ------------------------------------------------------
@@ -258,6 +336,7 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
       A2EPart p;
       p.val = bval; p.idx = bidx; p._pad = 0;
       ep[(int64_t)(cb + c) * nd.n_cchunks + lc] = p;
+      atomicMax(a.cmax + nd.cand_off + cb + c, (unsigned long long)__double_as_longlong(fabs(bval)));
     }
   }
 }
@@ -301,41 +380,43 @@ __global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_winner = 0x7fffffff;
   __syncthreads();
-  // candidates in blocks of 64 (8 per warp), in sequence order; lanes sweep the chunks (coalesced)
-  for (int c0 = 0; c0 < ncand; c0 += 64) {
-    for (int q = 0; q < 8; ++q) {
-      const int c = c0 + warp * 8 + q;
-      if (c >= ncand) break;
-      double bval = 0.0;
-      int bidx = 0x7fffffff;
-      for (int ch = lane; ch < nd.n_cchunks; ch += 32) {
-        const A2EPart p = ep[(int64_t)c * nd.n_cchunks + ch];
-        if (fabs(p.val) > fabs(bval) || (fabs(p.val) == fabs(bval) && p.idx < bidx)) { bval = p.val; bidx = p.idx; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, bval, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-        if (fabs(ov) > fabs(bval) || (fabs(ov) == fabs(bval) && oi < bidx)) { bval = ov; bidx = oi; }
-      }
-      if (lane == 0) {
-        s_val[c - c0] = bval;
-        s_idx[c - c0] = bidx;
-        if (!(fabs(bval) < 1e-14)) atomicMin(&s_winner, c);  // hodlr.h:191 (a NaN also leaves the loop, as there)
-      }
+  // first candidate (sequence order) whose max |residual| over all chunks is >= 1e-14 (hodlr.h:191; a NaN also
+  // leaves the reference's loop): the per-candidate maxima were reduced across chunks by atomicMax in a2_eval
+  {
+    const unsigned long long* cmax = a.cmax + nd.cand_off;
+    int mine = 0x7fffffff;
+    for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
+      const double m = __longlong_as_double((long long)cmax[c]);
+      if (!(m < 1e-14)) { mine = c; break; }
     }
-    __syncthreads();
-    if (s_winner != 0x7fffffff) break;
-    __syncthreads();
+    if (mine != 0x7fffffff) atomicMin(&s_winner, mine);
   }
+  __syncthreads();
+  if (s_winner != 0x7fffffff && warp == 0) {
+    const int c = s_winner;
+    double bval = 0.0;
+    int bidx = 0x7fffffff;
+    for (int ch = lane; ch < nd.n_cchunks; ch += 32) {
+      const A2EPart q = ep[(int64_t)c * nd.n_cchunks + ch];
+      if (fabs(q.val) > fabs(bval) || (fabs(q.val) == fabs(bval) && q.idx < bidx) || (q.val != q.val)) { bval = q.val; bidx = q.idx; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bval, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (fabs(ov) > fabs(bval) || (fabs(ov) == fabs(bval) && oi < bidx)) { bval = ov; bidx = oi; }
+    }
+    if (lane == 0) { s_val[c & 63] = bval; s_idx[c & 63] = bidx; }
+  }
+  __syncthreads();
   const int p = s_winner;
   // commit the stream: replay exactly the words consumed up to the winner (or the whole batch)
   mt_copy(&S.rng, &st.rng);
   __syncthreads();
-  if (threadIdx.x == 0) {
+  {
     const int w = (p != 0x7fffffff) ? words[p] : (ncand > 0 ? words[ncand - 1] : 0);
-    for (int q = 0; q < w; ++q) (void)mt_next(S.rng);
-    st.draws += w;
+    mt_skip_coop(S.rng, w);
+    if (threadIdx.x == 0) st.draws += w;
   }
   __syncthreads();
   mt_copy(&st.rng, &S.rng);
@@ -364,7 +445,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
   }
   __syncthreads();
   if (st.n_index == 0) return;
-  a2_generate(st, S, index, cand, cand_k, words, nd.bmax);
+  a2_generate(st, S, index, cand, cand_k, words, nd.bmax, a.cmax + nd.cand_off);
 }
 
 // ---- vnorm: normalised row residual -> panel column `rank`, partial ||v||^2 and V_prev^T v ----------------------
@@ -556,7 +637,8 @@ __global__ void __launch_bounds__(A2_THREADS) a2_finish_kernel(A2Args a) {
   }
   __syncthreads();
   if (s_done) return;
-  a2_generate(st, S, a.idx_ws + nd.idx_off, a.cand + nd.cand_off, a.cand_k + nd.cand_off, a.cand_words + nd.cand_off, nd.bmax);
+  a2_generate(st, S, a.idx_ws + nd.idx_off, a.cand + nd.cand_off, a.cand_k + nd.cand_off, a.cand_words + nd.cand_off, nd.bmax,
+              a.cmax + nd.cand_off);
 }
 
 // ---- dense fallback fill (hodlr.h:161-176): V = I, U = K(rows, cols) ---------------------------------------------
