@@ -31,6 +31,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FP64_TENSOR_PEAK_TFLOPS = 37.2   # DMMA.8x8x4 issue-bound peak measured on this pool (profiles/fp64_peaks_r01.txt)
+FP64_DFMA_PEAK_TFLOPS = 34.1     # DFMA issue-bound peak, same measurement
+# FP64 operations the specialised evaluator executes per covariance entry, counted in the SASS of
+# a2_eval_kernel<shape> (cuobjdump; DFMA = 2 flop, DMUL/DADD = 1; exp and sqrt are software sequences on this pipe)
+EVAL_FLOPS = {"cfg3": 56.0, "cfg2": 40.0, "cfg5": 120.0}
 HBM_FALLBACK_GBS = 6650.0
 
 
@@ -220,6 +224,7 @@ def run_ours(args):
         for p, a in ((dx, x), (dyerr, yerr), (dy, y)):
             _lib.check(lib.bgp_dev_alloc(C.byref(p), a.nbytes))
             _lib.check(lib.bgp_dev_upload(p, _lib.ptr(a), a.nbytes))
+        native.set_profiling(True)  # CUDA events around every a2_eval launch (the dominant kernel)
         opts = native._opts(wl["min_size"], wl["tol"], 42, "pernode", 0, 0, 1, exhaust)
         out = C.c_double()
 
@@ -244,7 +249,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = lib.bgp_launch_count()
-    t_steps, leaf_ms, aca_ms, up_ms, solve_ms = [], [], [], [], []
+    t_steps, leaf_ms, aca_ms, up_ms, solve_ms, aca_prof = [], [], [], [], [], []
     for _ in range(args.steps):
         flush_l2()
         barrier()
@@ -255,6 +260,7 @@ def run_ours(args):
         if world == 1:
             tm = native.timing()
             leaf_ms.append(tm["leaves_ms"]); aca_ms.append(tm["aca_ms"]); up_ms.append(tm["upsweep_ms"]); solve_ms.append(tm["solve_ms"])
+            aca_prof.append(native.aca_profile())
     barrier()
     launches = lib.bgp_launch_count() - launches0
     total = sum(t_steps)
@@ -319,18 +325,34 @@ def run_ours(args):
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if world == 1:
-        # dominant kernel of this workload: leaf_build_factor_kernel (batched leaf LDL^T, FP64 pipe bound)
-        m = wl["min_size"] if (wl["n"] // wl["min_size"]) & ((wl["n"] // wl["min_size"]) - 1) == 0 else None
+        # dominant kernel of this workload (profiles/launches_*_summary.txt): a2_eval_kernel — residual rows of the ACA
+        # candidates, FP64-pipe bound (software exp/sqrt + FMA updates; it writes only per-chunk maxima, so there is no
+        # HBM roofline).  Duration: CUDA events around every launch on its stream, inside the timed region.
         work = native.work()
-        leaf = int(work["leaf"])
-        n_leaves = n // leaf
-        flops = n_leaves * (leaf ** 3 / 3.0)
-        dur = statistics.mean(leaf_ms) * 1e-3
-        line["roofline"] = {"kernel": "leaf_build_factor_kernel", "bound": "tensor", "achieved": flops / dur * 1e-12,
-                            "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": flops / dur * 1e-12 / FP64_TENSOR_PEAK_TFLOPS,
-                            "traffic": None, "peak_source": "FP64 DMMA peak measured with tools/fp64_peaks.cu on this pool "
-                            "(MEASURED_PEAKS.json has no FP64 entry; hbm_gbs there = {0} [{1}])".format(peaks.get("hbm_gbs"), peaks_kind),
-                            "algorithmic_flops_per_launch": flops, "launch_ms": dur * 1e3}
+        ev_ms = statistics.mean(p["eval_ms"] for p in aca_prof)
+        launches_eval = statistics.mean(p["eval_launches"] for p in aca_prof)
+        evals = statistics.mean(p["evals"] for p in aca_prof)
+        fmas = statistics.mean(p["update_fmas"] for p in aca_prof)
+        flops = evals * EVAL_FLOPS[args.workload] + 2.0 * fmas
+        achieved = flops / (ev_ms * 1e-3) * 1e-12
+        traffic = None
+        try:
+            import csv
+            with open(os.path.join(ROOT, "profiles", "prof_a2_eval_r01_v1_raw.csv")) as fh:
+                rows = list(csv.reader(fh))
+            hdr = rows[0]
+            traffic = (float(rows[2][hdr.index("dram__bytes_read.sum")]) + float(rows[2][hdr.index("dram__bytes_write.sum")])) * 1e6
+        except Exception:
+            pass
+        line["roofline"] = {"kernel": "a2_eval_kernel", "bound": "tensor", "pipe": "fp64 (DFMA/DMUL/DADD; no matrix contraction in this kernel)",
+                            "achieved": achieved, "peak": FP64_DFMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_DFMA_PEAK_TFLOPS,
+                            "traffic": traffic,
+                            "peak_source": "FP64 DFMA issue peak measured with tools/fp64_peaks.cu on this pool, profiles/fp64_peaks_r01.txt "
+                            "(MEASURED_PEAKS.json has no FP64 entry; its hbm_gbs = {0} [{1}]; DMMA peak {2})".format(
+                                peaks.get("hbm_gbs"), peaks_kind, FP64_TENSOR_PEAK_TFLOPS),
+                            "algorithmic_flops_per_launch": flops / launches_eval, "launch_ms": ev_ms / launches_eval,
+                            "launches_per_step": launches_eval, "kernel_evals_per_step": evals,
+                            "flops_per_eval": EVAL_FLOPS[args.workload], "share_of_step": ev_ms / (1e3 * total / args.steps)}
         line["phases_ms"] = {"leaves": statistics.mean(leaf_ms), "aca": statistics.mean(aca_ms),
                              "upsweep": statistics.mean(up_ms), "solve": statistics.mean(solve_ms)}
         line["work"] = work

@@ -68,7 +68,10 @@ struct bgp_hodlr {
   DevBuf<A2State> d_a2states;
   DevBuf<A2EPart> d_epart;
   DevBuf<int> d_cand, d_cand_k, d_cand_words, d_cchunk_node, d_rchunk_node, d_nactive;
-  DevBuf<unsigned long long> d_cmax;
+  DevBuf<unsigned long long> d_cmax, d_stats;
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_events;
+  double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   DevBuf<double> d_vpart, d_upart;
   int aca_iters = 0;
   size_t w_cap = 0;
@@ -189,6 +192,8 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   BGP_TRY(h->d_vpart.reserve((size_t)ncc * (capmax + 1), s));
   BGP_TRY(h->d_upart.reserve((size_t)nrc * (capmax + 1), s));
   BGP_TRY(h->d_nactive.reserve(1, s));
+  BGP_TRY(h->d_stats.reserve(4, s));
+  BGP_CUDA(cudaMemsetAsync(h->d_stats.p, 0, sizeof(unsigned long long) * 4, s));
   BGP_CUDA(cudaMemcpyAsync(h->d_a2nodes.p, hn.data(), sizeof(A2Node) * nn, cudaMemcpyHostToDevice, s));
   BGP_CUDA(cudaMemcpyAsync(h->d_cchunk_node.p, cchunk_node.data(), sizeof(int) * ncc, cudaMemcpyHostToDevice, s));
   BGP_CUDA(cudaMemcpyAsync(h->d_rchunk_node.p, rchunk_node.data(), sizeof(int) * nrc, cudaMemcpyHostToDevice, s));
@@ -199,7 +204,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   a.idx_ws = h->d_idx.p; a.piv_rows = h->d_piv_rows.p; a.piv_cols = h->d_piv_cols.p;
   a.cand = h->d_cand.p; a.cand_k = h->d_cand_k.p; a.cand_words = h->d_cand_words.p; a.cmax = h->d_cmax.p; a.epart = h->d_epart.p;
   a.cchunk_node = h->d_cchunk_node.p; a.rchunk_node = h->d_rchunk_node.p; a.vpart = h->d_vpart.p; a.upart = h->d_upart.p;
-  a.capmax = capmax; a.n_active = h->d_nactive.p;
+  a.capmax = capmax; a.n_active = h->d_nactive.p; a.stats = h->d_stats.p;
   static bool a2_attr = false;
   if (!a2_attr) {
     cudaFuncSetAttribute(a2_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A2NodeSmem));
@@ -212,7 +217,16 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   int active = nn, iters = 0;
   while (active > 0) {
     for (int rep = 0; rep < 8; ++rep) {
-      a2_eval_kernel<<<dim3(ncc, A2_GROUPS), A2_THREADS, 0, s>>>(a);
+      if (h->profile) {
+        if (h->prof_events.size() < (size_t)(2 * (iters + 1))) {
+          cudaEvent_t e0, e1;
+          BGP_CUDA(cudaEventCreate(&e0)); BGP_CUDA(cudaEventCreate(&e1));
+          h->prof_events.push_back(e0); h->prof_events.push_back(e1);
+        }
+        BGP_CUDA(cudaEventRecord(h->prof_events[2 * iters], s));
+      }
+      a2_eval_launch(h->prog.shape, dim3(ncc, A2_GROUPS), s, a);
+      if (h->profile) BGP_CUDA(cudaEventRecord(h->prof_events[2 * iters + 1], s));
       BGP_LAUNCH_CHECK();
       a2_decide_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), s>>>(a);
       BGP_LAUNCH_CHECK();
@@ -229,6 +243,17 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
     if (iters > (1 << 22)) { set_error("ACA did not terminate"); return BGP_ERR_CUDA; }
   }
   h->aca_iters = iters;
+  {
+    unsigned long long st4[4] = {0, 0, 0, 0};
+    BGP_CUDA(cudaMemcpyAsync(st4, h->d_stats.p, sizeof(st4), cudaMemcpyDeviceToHost, s));
+    BGP_CUDA(cudaStreamSynchronize(s));
+    h->prof[1] = iters; h->prof[2] = (double)st4[0]; h->prof[3] = (double)st4[1]; h->prof[4] = (double)st4[2];
+    if (h->profile) {
+      double tot = 0.0;
+      for (int i = 0; i < iters; ++i) { float ms = 0; cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]); tot += ms; }
+      h->prof[0] = tot;
+    }
+  }
   if (h->opts.exhaust_mode == BGP_EXHAUST_DENSE) {
     a2_dense_fill_kernel<<<dim3(nn, 64), 256, 0, s>>>(a);
     BGP_LAUNCH_CHECK();
@@ -585,6 +610,7 @@ void bgp_hodlr_destroy(bgp_hodlr_t* h) {
   h->d_a2nodes.release(); h->d_a2states.release(); h->d_epart.release(); h->d_cand.release(); h->d_cand_k.release();
   h->d_cand_words.release(); h->d_cchunk_node.release(); h->d_rchunk_node.release(); h->d_nactive.release();
   h->d_vpart.release(); h->d_upart.release(); h->d_cmax.release();
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   if (h->sA) {
     cudaStreamSynchronize(h->sA); cudaStreamSynchronize(h->sB);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
@@ -710,6 +736,16 @@ int bgp_hodlr_node_pivots(const bgp_hodlr_t* hc, int64_t node, int32_t* rows, in
 int bgp_hodlr_last_timing(const bgp_hodlr_t* h, double* ms5) {
   if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
   for (int i = 0; i < 5; ++i) ms5[i] = h->t_ms[i];
+  return BGP_OK;
+}
+int bgp_hodlr_set_profiling(bgp_hodlr_t* h, int on) {
+  if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
+  h->profile = on != 0;
+  return BGP_OK;
+}
+int bgp_hodlr_last_aca_profile(const bgp_hodlr_t* h, double* p5) {
+  if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
+  for (int i = 0; i < 5; ++i) p5[i] = h->prof[i];
   return BGP_OK;
 }
 int bgp_hodlr_last_work(const bgp_hodlr_t* h, double* w6) {

@@ -221,6 +221,7 @@ struct A2Args {
   double* upart;   // per row chunk
   int capmax;
   int* n_active;
+  unsigned long long* stats;  // [0] candidate-row kernel evaluations, [1] residual-update FMAs, [2] candidates, [3] accepted
 };
 
 // ---- init: index list, RNG seed, first candidates -------------------------------------------------------------
@@ -341,7 +342,9 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
   }
 }
 
-__global__ void __launch_bounds__(A2_THREADS, 2) a2_eval_kernel(A2Args a) {
+// one instantiation per program shape: the specialised ones carry no interpreter and need far fewer registers
+template <int SHAPE>
+__global__ void __launch_bounds__(A2_THREADS, (SHAPE == BGP_SHAPE_GENERIC) ? 2 : 3) a2_eval_kernel(A2Args a) {
   __shared__ DevProgram P;
   __shared__ double s_x[A2_CG][ACA_MAX_NDIM];
   __shared__ double s_u[A2_CG][128 + 1];  // U(i, k) for a k-tile of 128
@@ -357,7 +360,22 @@ __global__ void __launch_bounds__(A2_THREADS, 2) a2_eval_kernel(A2Args a) {
   const int rank = st.rank;
   __syncthreads();
   const int ndim = P.ndim;
-  BGP_DISPATCH_SHAPE(P, a2_eval_body(a, nd, rank, ncand, ndim, fn, s_x, s_u, s_red, s_redi));
+  if constexpr (SHAPE == BGP_SHAPE_GENERIC) {
+    GenericKernelFn fn{&P};
+    a2_eval_body(a, nd, rank, ncand, ndim, fn, s_x, s_u, s_red, s_redi);
+  } else {
+    ScaledProfile1D<SHAPE> fn{P.sc, P.sm};
+    a2_eval_body(a, nd, rank, ncand, 1, fn, s_x, s_u, s_red, s_redi);
+  }
+}
+inline void a2_eval_launch(int shape, dim3 grid, cudaStream_t s, const A2Args& a) {
+  switch (shape) {
+    case BGP_SHAPE_EXPSQ: a2_eval_kernel<BGP_SHAPE_EXPSQ><<<grid, A2_THREADS, 0, s>>>(a); break;
+    case BGP_SHAPE_M32: a2_eval_kernel<BGP_SHAPE_M32><<<grid, A2_THREADS, 0, s>>>(a); break;
+    case BGP_SHAPE_M52: a2_eval_kernel<BGP_SHAPE_M52><<<grid, A2_THREADS, 0, s>>>(a); break;
+    case BGP_SHAPE_EXP: a2_eval_kernel<BGP_SHAPE_EXP><<<grid, A2_THREADS, 0, s>>>(a); break;
+    default: a2_eval_kernel<BGP_SHAPE_GENERIC><<<grid, A2_THREADS, 0, s>>>(a); break;
+  }
 }
 
 // ---- decide: first usable candidate wins; commit the RNG / index list up to it ----------------------------------
@@ -378,7 +396,12 @@ __global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
   int* words = a.cand_words + nd.cand_off;
   int* index = a.idx_ws + nd.idx_off;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_winner = 0x7fffffff;
+  if (threadIdx.x == 0) {
+    s_winner = 0x7fffffff;
+    atomicAdd(a.stats + 0, (unsigned long long)ncand * (unsigned long long)nd.n_cols);
+    atomicAdd(a.stats + 1, (unsigned long long)ncand * (unsigned long long)nd.n_cols * (unsigned long long)st.rank);
+    atomicAdd(a.stats + 2, (unsigned long long)ncand);
+  }
   __syncthreads();
   // first candidate (sequence order) whose max |residual| over all chunks is >= 1e-14 (hodlr.h:191; a NaN also
   // leaves the reference's loop): the per-candidate maxima were reduced across chunks by atomicMax in a2_eval

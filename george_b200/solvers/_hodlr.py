@@ -117,6 +117,14 @@ class HODLRSolver(object):
         _lib.check(self._lib.bgp_hodlr_last_timing(self._ptr, t))
         return dict(zip(("leaves_ms", "aca_ms", "upsweep_ms", "compute_ms", "solve_ms"), list(t)))
 
+    def set_profiling(self, on=True):
+        _lib.check(self._lib.bgp_hodlr_set_profiling(self._ptr, 1 if on else 0))
+
+    def aca_profile(self):
+        p = (C.c_double * 5)()
+        _lib.check(self._lib.bgp_hodlr_last_aca_profile(self._ptr, p))
+        return dict(zip(("eval_ms", "eval_launches", "evals", "update_fmas", "candidates"), list(p)))
+
     def work(self):
         w = (C.c_double * 6)()
         _lib.check(self._lib.bgp_hodlr_last_work(self._ptr, w))

@@ -229,6 +229,11 @@ int bgp_hodlr_last_timing(const bgp_hodlr_t* h, double* ms5);
 /* Algorithmic work of the last compute: [0] kernel evaluations, [1] bytes, [2] flops,
  * [3] sum of per-level max ranks R, [4] leaf size m, [5] number of levels. */
 int bgp_hodlr_last_work(const bgp_hodlr_t* h, double* w6);
+/* Optional per-kernel timing of the ACA's dominant kernel (a2_eval_kernel): with profiling on, every launch is
+ * bracketed by CUDA events on its stream.  p5 = [0] summed launch time ms, [1] launches (= lock-step iterations),
+ * [2] candidate-row kernel evaluations, [3] residual-update FMAs, [4] candidate rows examined. */
+int bgp_hodlr_set_profiling(bgp_hodlr_t* h, int on);
+int bgp_hodlr_last_aca_profile(const bgp_hodlr_t* h, double* p5);
 
 /* Multi-GPU exchange step: after the local sub-tree is factored, the rows this
  * shard owns of the shared top-level factor panel are exported, all-gathered by the host
