@@ -174,9 +174,9 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
     a.rchunk0 = (int)rchunk_node.size(); a.n_rchunks = (d.n_rows + A2_CHUNK - 1) / A2_CHUNK;
     for (int c = 0; c < a.n_cchunks; ++c) cchunk_node.push_back(i);
     for (int c = 0; c < a.n_rchunks; ++c) rchunk_node.push_back(i);
-    a.bmax = std::min(A2_BMAX, d.n_rows); a._pad = 0;
+    a.bmax = std::min(A2_BMAX, d.n_rows);
     a.cand_off = cand_total; cand_total += a.bmax;
-    a.epart_off = epart_total; epart_total += (int64_t)a.bmax * a.n_cchunks;
+    a.epart_off = 0; a.is_top = 0;
     capmax = std::max(capmax, d.cap);
   }
   const int ncc = (int)cchunk_node.size(), nrc = (int)rchunk_node.size();
@@ -186,7 +186,8 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   BGP_TRY(h->d_cand_k.reserve((size_t)cand_total, s));
   BGP_TRY(h->d_cand_words.reserve((size_t)cand_total, s));
   BGP_TRY(h->d_cmax.reserve((size_t)cand_total, s));
-  BGP_TRY(h->d_epart.reserve((size_t)epart_total, s));
+  (void)epart_total;
+  BGP_TRY(h->d_epart.reserve((size_t)std::max(ncc, 1), s));
   BGP_TRY(h->d_cchunk_node.reserve(ncc, s));
   BGP_TRY(h->d_rchunk_node.reserve(nrc, s));
   BGP_TRY(h->d_vpart.reserve((size_t)ncc * (capmax + 1), s));
@@ -205,6 +206,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   a.cand = h->d_cand.p; a.cand_k = h->d_cand_k.p; a.cand_words = h->d_cand_words.p; a.cmax = h->d_cmax.p; a.epart = h->d_epart.p;
   a.cchunk_node = h->d_cchunk_node.p; a.rchunk_node = h->d_rchunk_node.p; a.vpart = h->d_vpart.p; a.upart = h->d_upart.p;
   a.capmax = capmax; a.n_active = h->d_nactive.p; a.stats = h->d_stats.p;
+  a.shard_rank = 0; a.shard_count = 1;
   static bool a2_attr = false;
   if (!a2_attr) {
     cudaFuncSetAttribute(a2_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A2NodeSmem));
@@ -230,9 +232,11 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
       BGP_LAUNCH_CHECK();
       a2_decide_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), s>>>(a);
       BGP_LAUNCH_CHECK();
-      a2_vnorm_kernel<<<ncc, A2_THREADS, 0, s>>>(a);
+      a2_vrow_kernel<<<ncc, A2_THREADS, 0, s>>>(a);
       BGP_LAUNCH_CHECK();
-      a2_ucol_kernel<<<nrc, A2_THREADS, 0, s>>>(a);
+      a2_pivot_kernel<<<nn, 32, 0, s>>>(a);
+      BGP_LAUNCH_CHECK();
+      a2_vnorm_ucol_kernel<<<ncc + nrc, A2_THREADS, 0, s>>>(a, ncc);
       BGP_LAUNCH_CHECK();
       a2_finish_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), s>>>(a);
       BGP_LAUNCH_CHECK();
@@ -609,7 +613,7 @@ void bgp_hodlr_destroy(bgp_hodlr_t* h) {
   h->d_ticket.release(); h->d_chain_done.release(); h->d_ncols_by_depth.release(); h->d_chain_state.release();
   h->d_a2nodes.release(); h->d_a2states.release(); h->d_epart.release(); h->d_cand.release(); h->d_cand_k.release();
   h->d_cand_words.release(); h->d_cchunk_node.release(); h->d_rchunk_node.release(); h->d_nactive.release();
-  h->d_vpart.release(); h->d_upart.release(); h->d_cmax.release();
+  h->d_vpart.release(); h->d_upart.release(); h->d_cmax.release(); h->d_stats.release();
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   if (h->sA) {
     cudaStreamSynchronize(h->sA); cudaStreamSynchronize(h->sB);

@@ -29,7 +29,7 @@ struct A2Node {  // static description
   int row0, n_rows, col0, n_cols;
   int vcol, cap, pre_id, node;
   int cchunk0, n_cchunks, rchunk0, n_rchunks;
-  int bmax, _pad;
+  int bmax, is_top;  // is_top: node above the shard cut, its candidate scan is split across ranks by column chunk
   int64_t idx_off, piv_off, cand_off, epart_off;
 };
 
@@ -221,6 +221,7 @@ struct A2Args {
   double* upart;   // per row chunk
   int capmax;
   int* n_active;
+  int shard_rank, shard_count;  // multi-GPU: top nodes' column chunks are dealt round-robin to the ranks
   unsigned long long* stats;  // [0] candidate-row kernel evaluations, [1] residual-update FMAs, [2] candidates, [3] accepted
 };
 
@@ -262,7 +263,6 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
   const double* xr = a.x + (int64_t)nd.row0 * ndim;
   const double* xc = a.x + (int64_t)(nd.col0 + c_lo) * ndim;
   const int* cand = a.cand + nd.cand_off;
-  A2EPart* ep = a.epart + nd.epart_off;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   for (int cb = blockIdx.y * A2_CG; cb < ncand; cb += A2_GROUPS * A2_CG) {
@@ -334,9 +334,7 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
         const int oi = s_redi[c][w];
         if (fabs(ov) > fabs(bval) || (fabs(ov) == fabs(bval) && oi < bidx)) { bval = ov; bidx = oi; }
       }
-      A2EPart p;
-      p.val = bval; p.idx = bidx; p._pad = 0;
-      ep[(int64_t)(cb + c) * nd.n_cchunks + lc] = p;
+      (void)bidx;
       atomicMax(a.cmax + nd.cand_off + cb + c, (unsigned long long)__double_as_longlong(fabs(bval)));
     }
   }
@@ -356,6 +354,8 @@ __global__ void __launch_bounds__(A2_THREADS, (SHAPE == BGP_SHAPE_GENERIC) ? 2 :
   const int ncand = st.ncand;
   if (ncand <= (int)blockIdx.y * A2_CG) return;
   const A2Node nd = a.nodes[nid];
+  // sharded run: the scan of a top node is dealt out by column chunk; the per-candidate maxima are all-reduced (MAX)
+  if (nd.is_top && a.shard_count > 1 && ((int)(blockIdx.x - nd.cchunk0) % a.shard_count) != a.shard_rank) return;
   stage_program(&P, a.prog);
   const int rank = st.rank;
   __syncthreads();
@@ -383,14 +383,11 @@ __global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
   extern __shared__ __align__(16) unsigned char a2_smem_raw[];
   A2NodeSmem& S = *reinterpret_cast<A2NodeSmem*>(a2_smem_raw);
   __shared__ int s_winner;
-  __shared__ double s_val[64];
-  __shared__ int s_idx[64];
   const int nid = blockIdx.x;
   A2State& st = a.states[nid];
   if (st.phase != A2_SELECT || !st.active) return;
   const A2Node nd = a.nodes[nid];
   const int ncand = st.ncand;
-  const A2EPart* ep = a.epart + nd.epart_off;
   int* cand = a.cand + nd.cand_off;
   int* cand_k = a.cand_k + nd.cand_off;
   int* words = a.cand_words + nd.cand_off;
@@ -415,23 +412,6 @@ __global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
     if (mine != 0x7fffffff) atomicMin(&s_winner, mine);
   }
   __syncthreads();
-  if (s_winner != 0x7fffffff && warp == 0) {
-    const int c = s_winner;
-    double bval = 0.0;
-    int bidx = 0x7fffffff;
-    for (int ch = lane; ch < nd.n_cchunks; ch += 32) {
-      const A2EPart q = ep[(int64_t)c * nd.n_cchunks + ch];
-      if (fabs(q.val) > fabs(bval) || (fabs(q.val) == fabs(bval) && q.idx < bidx) || (q.val != q.val)) { bval = q.val; bidx = q.idx; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, bval, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-      if (fabs(ov) > fabs(bval) || (fabs(ov) == fabs(bval) && oi < bidx)) { bval = ov; bidx = oi; }
-    }
-    if (lane == 0) { s_val[c & 63] = bval; s_idx[c & 63] = bidx; }
-  }
-  __syncthreads();
   const int p = s_winner;
   // commit the stream: replay exactly the words consumed up to the winner (or the whole batch)
   mt_copy(&S.rng, &st.rng);
@@ -450,9 +430,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
       for (int c = ncand - 1; c > p; --c) index[cand_k[c]] = cand[c];
       st.n_index -= (p + 1);
       st.piv_i = cand[p];
-      st.piv_j = s_idx[p & 63];
-      st.pivot = s_val[p & 63];
-      st.phase = A2_ACCEPT;
+      st.phase = A2_ACCEPT;  // pivot column / value follow from a2_vrow + a2_pivot
       st.B = max(1, min(st.B, 2 * (p + 1)));
     }
     return;
@@ -471,13 +449,14 @@ __global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
   a2_generate(st, S, index, cand, cand_k, words, nd.bmax, a.cmax + nd.cand_off);
 }
 
-// ---- vnorm: normalised row residual -> panel column `rank`, partial ||v||^2 and V_prev^T v ----------------------
-__global__ void __launch_bounds__(A2_THREADS) a2_vnorm_kernel(A2Args a) {
+// ---- vrow: residual of the winning row over one column chunk, stored UN-normalised in panel column `rank`, plus the
+//      chunk's arg-max (hodlr.h:186-189).  Every rank does this for every node (it is one row per accepted pivot).
+__global__ void __launch_bounds__(A2_THREADS) a2_vrow_kernel(A2Args a) {
   __shared__ DevProgram P;
   __shared__ double s_x[ACA_MAX_NDIM];
   __shared__ double s_u[128];
-  __shared__ double s_v[A2_CHUNK];
-  __shared__ double red[32];
+  __shared__ double s_red[A2_THREADS / 32];
+  __shared__ int s_redi[A2_THREADS / 32];
   const int chunk = blockIdx.x;
   const int nid = a.cchunk_node[chunk];
   const A2State& st = a.states[nid];
@@ -492,7 +471,6 @@ __global__ void __launch_bounds__(A2_THREADS) a2_vnorm_kernel(A2Args a) {
   double* Vcols = a.Vp + (int64_t)nd.vcol * a.ld;
   const double* xc = a.x + (int64_t)(nd.col0 + c_lo) * ndim;
   const int i = st.piv_i;
-  const double pivot = st.pivot;
   for (int q = threadIdx.x; q < ndim; q += A2_THREADS) s_x[q] = a.x[(int64_t)(nd.row0 + i) * ndim + q];
   __syncthreads();
   double vals[A2_EPT];
@@ -515,13 +493,81 @@ __global__ void __launch_bounds__(A2_THREADS) a2_vnorm_kernel(A2Args a) {
       }
     }
   }
+  double best = -1.0, bval = 0.0;
+  int bidx = 0x7fffffff;
+#pragma unroll
+  for (int e = 0; e < A2_EPT; ++e) {
+    const int n = threadIdx.x + e * A2_THREADS;
+    if (n < c_n) {
+      Vcols[(int64_t)rank * a.ld + nd.col0 + c_lo + n] = vals[e];
+      const double av = fabs(vals[e]);
+      if (av > best) { best = av; bidx = c_lo + n; bval = vals[e]; }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const double ov = __shfl_xor_sync(0xffffffffu, bval, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; bval = ov; }
+  }
+  if (lane == 0) { s_red[warp] = bval; s_redi[warp] = bidx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < A2_THREADS / 32; ++w) {
+      const double ov = s_red[w];
+      const int oi = s_redi[w];
+      if (fabs(ov) > fabs(bval) || (fabs(ov) == fabs(bval) && oi < bidx) || (ov != ov)) { bval = ov; bidx = oi; }
+    }
+    A2EPart p;
+    p.val = bval; p.idx = bidx; p._pad = 0;
+    a.epart[nd.cchunk0 + lc] = p;  // one slot per column chunk
+  }
+}
+
+// ---- pivot: arg-max over the chunks of the winning row (first maximum, as Eigen's maxCoeff) ------------------------
+__global__ void __launch_bounds__(32) a2_pivot_kernel(A2Args a) {
+  const int nid = blockIdx.x;
+  A2State& st = a.states[nid];
+  if (st.phase != A2_ACCEPT || !st.active) return;
+  const A2Node nd = a.nodes[nid];
+  const int lane = threadIdx.x;
+  double bval = 0.0;
+  int bidx = 0x7fffffff;
+  for (int ch = lane; ch < nd.n_cchunks; ch += 32) {
+    const A2EPart q = a.epart[nd.cchunk0 + ch];
+    if (fabs(q.val) > fabs(bval) || (fabs(q.val) == fabs(bval) && q.idx < bidx) || (q.val != q.val)) { bval = q.val; bidx = q.idx; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bval, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (fabs(ov) > fabs(bval) || (fabs(ov) == fabs(bval) && oi < bidx) || (ov != ov)) { bval = ov; bidx = oi; }
+  }
+  if (lane == 0) { st.piv_j = bidx; st.pivot = bval; }
+}
+
+// ---- vnorm: normalise the stored row residual (hodlr.h:194), partial ||v||^2 and V_prev^T v -----------------------
+__device__ __forceinline__ void a2_vnorm_body(const A2Args& a, int chunk, double* s_v, double* red) {
+  const int nid = a.cchunk_node[chunk];
+  const A2State& st = a.states[nid];
+  if (st.phase != A2_ACCEPT || !st.active) return;
+  const A2Node nd = a.nodes[nid];
+  const int rank = st.rank;
+  const int lc = chunk - nd.cchunk0;
+  const int c_lo = lc * A2_CHUNK;
+  const int c_n = min(A2_CHUNK, nd.n_cols - c_lo);
+  double* Vcols = a.Vp + (int64_t)nd.vcol * a.ld;
+  const double pivot = st.pivot;
   double vn2 = 0.0;
 #pragma unroll
   for (int e = 0; e < A2_EPT; ++e) {
     const int n = threadIdx.x + e * A2_THREADS;
     if (n < c_n) {
-      const double v = vals[e] / pivot;  // hodlr.h:194
-      Vcols[(int64_t)rank * a.ld + nd.col0 + c_lo + n] = v;
+      double* pv = Vcols + (int64_t)rank * a.ld + nd.col0 + c_lo + n;
+      const double v = *pv / pivot;
+      *pv = v;
       s_v[n] = v;
       vn2 += v * v;
     }
@@ -540,13 +586,16 @@ __global__ void __launch_bounds__(A2_THREADS) a2_vnorm_kernel(A2Args a) {
 }
 
 // ---- ucol: column residual -> panel column `rank` (row part), partial ||u||^2 and U_prev^T u --------------------
-__global__ void __launch_bounds__(A2_THREADS) a2_ucol_kernel(A2Args a) {
+// vnorm (column chunks) and ucol (row chunks) are independent: one launch, blocks [0, n_cchunks) normalise, the rest
+// compute the column residual.
+__global__ void __launch_bounds__(A2_THREADS) a2_vnorm_ucol_kernel(A2Args a, int n_cchunks_total) {
   __shared__ DevProgram P;
   __shared__ double s_x[ACA_MAX_NDIM];
   __shared__ double s_vr[128];
   __shared__ double s_u[A2_CHUNK];
   __shared__ double red[32];
-  const int chunk = blockIdx.x;
+  if ((int)blockIdx.x < n_cchunks_total) { a2_vnorm_body(a, blockIdx.x, s_u, red); return; }
+  const int chunk = blockIdx.x - n_cchunks_total;
   const int nid = a.rchunk_node[chunk];
   const A2State& st = a.states[nid];
   if (st.phase != A2_ACCEPT || !st.active) return;
