@@ -21,7 +21,7 @@ LIBDIR = os.path.join(_HERE, "lib")
 LIB = os.path.join(LIBDIR, "libbgp_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
-SOURCES = ["core.cu", "kmat.cu", "dense.cu", "hodlr.cu"]
+SOURCES = ["core.cu", "kmat.cu", "dense.cu", "hodlr.cu", "comm.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -81,7 +81,7 @@ def build(force=False, verbose=False):
         with ThreadPoolExecutor(max_workers=min(4, len(jobs))) as ex:
             list(ex.map(compile_one, jobs))
     if jobs or not os.path.exists(LIB):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout)

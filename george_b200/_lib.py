@@ -92,6 +92,10 @@ SIGNATURES = {
     "bgp_hodlr_import_top": (C.c_int, [_p, _p, _i64]),
     "bgp_hodlr_shard_rows": (C.c_int, [_p, _i32, C.POINTER(_i64), C.POINTER(_i64)]),
     "bgp_hodlr_finish_top": (C.c_int, [_p]),
+    "bgp_comm_unique_id": (C.c_int, [_p, C.c_char_p]),
+    "bgp_comm_init": (C.c_int, [_p, C.c_int, C.c_int, C.c_char_p]),
+    "bgp_comm_destroy": (C.c_int, []),
+    "bgp_comm_size": (C.c_int, []),
     "bgp_hodlr_solve_local_dev": (C.c_int, [_p, _p, _i64, _i64]),
     "bgp_hodlr_solve_top_dev": (C.c_int, [_p, _p, _i64, _i64]),
     "bgp_dev_alloc": (C.c_int, [C.POINTER(_p), C.c_size_t]),

@@ -19,6 +19,10 @@
 
 namespace bgp {
 int upload_program(const DevProgram& P, DevBuf<DevProgram>& buf, cudaStream_t s);
+bool comm_ready();
+int comm_rank();
+int comm_world();
+int comm_allreduce_max_u64(unsigned long long* buf, size_t count, cudaStream_t s);
 }
 using namespace bgp;
 
@@ -162,7 +166,9 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   if (nn == 0) return BGP_OK;
   std::vector<A2Node> hn(nn);
   std::vector<int> cchunk_node, rchunk_node;
-  int64_t cand_total = 0, epart_total = 0;
+  int64_t cand_total = 0, epart_total = 0, top_cand_total = 0;
+  // distributed scan of the nodes above the shard cut (needs the in-loop communicator; descs list those nodes first)
+  const bool dist_top = h->opts.shard_count > 1 && comm_ready() && comm_world() == h->opts.shard_count;
   int capmax = 1;
   for (int i = 0; i < nn; ++i) {
     const AcaDesc& d = descs[i];
@@ -176,7 +182,8 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
     for (int c = 0; c < a.n_rchunks; ++c) rchunk_node.push_back(i);
     a.bmax = std::min(A2_BMAX, d.n_rows);
     a.cand_off = cand_total; cand_total += a.bmax;
-    a.epart_off = 0; a.is_top = 0;
+    a.epart_off = 0; a.is_top = (dist_top && h->nodes[d.pre_id].top) ? 1 : 0;
+    if (a.is_top) top_cand_total = cand_total;
     capmax = std::max(capmax, d.cap);
   }
   const int ncc = (int)cchunk_node.size(), nrc = (int)rchunk_node.size();
@@ -192,7 +199,9 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   BGP_TRY(h->d_rchunk_node.reserve(nrc, s));
   BGP_TRY(h->d_vpart.reserve((size_t)ncc * (capmax + 1), s));
   BGP_TRY(h->d_upart.reserve((size_t)nrc * (capmax + 1), s));
-  BGP_TRY(h->d_nactive.reserve(1, s));
+  BGP_TRY(h->d_nactive.reserve(2, s));
+  int n_top = 0;
+  for (int i = 0; i < nn; ++i) n_top += hn[i].is_top;
   BGP_TRY(h->d_stats.reserve(4, s));
   BGP_CUDA(cudaMemsetAsync(h->d_stats.p, 0, sizeof(unsigned long long) * 4, s));
   BGP_CUDA(cudaMemcpyAsync(h->d_a2nodes.p, hn.data(), sizeof(A2Node) * nn, cudaMemcpyHostToDevice, s));
@@ -206,7 +215,8 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   a.cand = h->d_cand.p; a.cand_k = h->d_cand_k.p; a.cand_words = h->d_cand_words.p; a.cmax = h->d_cmax.p; a.epart = h->d_epart.p;
   a.cchunk_node = h->d_cchunk_node.p; a.rchunk_node = h->d_rchunk_node.p; a.vpart = h->d_vpart.p; a.upart = h->d_upart.p;
   a.capmax = capmax; a.n_active = h->d_nactive.p; a.stats = h->d_stats.p;
-  a.shard_rank = 0; a.shard_count = 1;
+  a.shard_rank = dist_top ? h->opts.shard_rank : 0; a.shard_count = dist_top ? h->opts.shard_count : 1;
+  if (dist_top) BGP_CUDA(cudaMemcpyAsync(h->d_nactive.p + 1, &n_top, sizeof(int), cudaMemcpyHostToDevice, s));
   static bool a2_attr = false;
   if (!a2_attr) {
     cudaFuncSetAttribute(a2_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A2NodeSmem));
@@ -217,6 +227,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   a2_init_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), s>>>(a);
   BGP_LAUNCH_CHECK();
   int active = nn, iters = 0;
+  bool top_active = dist_top && n_top > 0;  // identical on every rank: the top nodes take identical decisions
   while (active > 0) {
     for (int rep = 0; rep < 8; ++rep) {
       if (h->profile) {
@@ -229,6 +240,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
       }
       a2_eval_launch(h->prog.shape, dim3(ncc, A2_GROUPS), s, a);
       if (h->profile) BGP_CUDA(cudaEventRecord(h->prof_events[2 * iters + 1], s));
+      if (top_active) BGP_TRY(comm_allreduce_max_u64(h->d_cmax.p, (size_t)top_cand_total, s));
       BGP_LAUNCH_CHECK();
       a2_decide_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), s>>>(a);
       BGP_LAUNCH_CHECK();
@@ -242,8 +254,11 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
       BGP_LAUNCH_CHECK();
       iters++;
     }
-    BGP_CUDA(cudaMemcpyAsync(&active, h->d_nactive.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    int act2[2] = {0, 0};
+    BGP_CUDA(cudaMemcpyAsync(act2, h->d_nactive.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
     BGP_CUDA(cudaStreamSynchronize(s));
+    active = act2[0];
+    if (dist_top) top_active = act2[1] > 0;
     if (iters > (1 << 22)) { set_error("ACA did not terminate"); return BGP_ERR_CUDA; }
   }
   h->aca_iters = iters;
@@ -411,7 +426,11 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
     std::vector<int> order(nint);
     for (int i = 0; i < nint; ++i) order[i] = i;
     if (o.rng_mode == BGP_RNG_REFERENCE) std::sort(order.begin(), order.end(), [&](int a, int b) { return hdesc[a].pre_id < hdesc[b].pre_id; });
-    else std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return hdesc[a].n_rows > hdesc[b].n_rows; });
+    else std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      const int ta = h->nodes[hdesc[a].pre_id].top, tb = h->nodes[hdesc[b].pre_id].top;
+      if (ta != tb) return ta > tb;  // nodes above the shard cut first (contiguous candidate range for the all-reduce)
+      return hdesc[a].n_rows > hdesc[b].n_rows;
+    });
     std::vector<AcaDesc> hdesc_sorted(nint);
     for (int i = 0; i < nint; ++i) hdesc_sorted[i] = hdesc[order[i]];
 

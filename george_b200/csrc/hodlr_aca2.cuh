@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_init_kernel(A2Args a) {
   mt_copy(&st.rng, &S.rng);  // committed = state before the speculative draws
   __syncthreads();
   if (nd.cap <= 0) {
-    if (threadIdx.x == 0) { st.status = 1; st.phase = A2_DONE; st.active = 0; atomicSub(a.n_active, 1); }
+    if (threadIdx.x == 0) { st.status = 1; st.phase = A2_DONE; st.active = 0; { atomicSub(a.n_active, 1); if (nd.is_top) atomicSub(a.n_active + 1, 1); } }
     return;
   }
   a2_generate(st, S, index, a.cand + nd.cand_off, a.cand_k + nd.cand_off, a.cand_words + nd.cand_off, nd.bmax,
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
     if (st.n_index == 0) {
       st.fallback = 1;  // rows exhausted (hodlr.h:161); dense fill (if requested) happens after the loop
       st.phase = A2_DONE; st.active = 0;
-      atomicSub(a.n_active, 1);
+      { atomicSub(a.n_active, 1); if (nd.is_top) atomicSub(a.n_active + 1, 1); }
     }
   }
   __syncthreads();
@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_finish_kernel(A2Args a) {
     }
     if (done) {
       st.phase = A2_DONE; st.active = 0;
-      atomicSub(a.n_active, 1);
+      { atomicSub(a.n_active, 1); if (nd.is_top) atomicSub(a.n_active + 1, 1); }
     } else {
       st.phase = A2_SELECT;
     }

@@ -65,6 +65,41 @@ def allgather_padded(local, rows_pad, group=None):
     return out
 
 
+_COMM_WORLD = 0
+
+
+def ensure_device_comm(group=None):
+    """Create (once) the NCCL communicator that libbgp_b200 uses INSIDE its ACA loop (``csrc/comm.cu``): rank 0 makes
+    the unique id, it is broadcast over the host's process group, every rank initialises.  Returns the world size."""
+    global _COMM_WORLD
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1 or _COMM_WORLD == world:
+        return world
+    lib = _lib.load()
+    rank = dist.get_rank(group)
+    buf = (C.c_ubyte * 128)()
+    path = None
+    try:
+        import nvidia.nccl
+        import glob
+        import os
+        hits = glob.glob(os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so*"))
+        path = hits[0].encode() if hits else None
+    except Exception:
+        path = None
+    if rank == 0:
+        _lib.check(lib.bgp_comm_unique_id(buf, path))
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0, group=group)
+    ident = (C.c_ubyte * 128)(*t.cpu().tolist())
+    _lib.check(lib.bgp_comm_init(ident, rank, world, path))
+    _COMM_WORLD = world
+    return world
+
+
 class ShardedHODLRSolver(object):
     """Solver plugin with the ``HODLRSolver`` surface whose ``compute``/``dot_solve`` are collective over a
     ``torch.distributed`` process group (one rank per GPU).  ``x``, ``yerr`` and ``y`` are replicated on every rank."""
@@ -99,6 +134,7 @@ class ShardedHODLRSolver(object):
         if self._ranges is None:
             raise ValueError("the HODLR tree (N={0}, min_size={1}) is too shallow to shard {2} ways".format(
                 self._n, self.min_size, world))
+        ensure_device_comm(self.group)  # lets the top-level candidate scans be split across the ranks
         self.solver = Native()
         self.solver.compute(self.kernel, x, yerr, self.min_size, self.tol, self.seed, rank_capacity=self.rank_capacity,
                             shard_rank=rank, shard_count=world, exhaust=self.exhaust)

@@ -248,6 +248,15 @@ int bgp_hodlr_import_top(bgp_hodlr_t* h, const double* all_buf_dev, int64_t rows
 /* row range [row0, row0+rows) owned by shard `s` (same on every shard; -1 rows if the tree cannot be cut) */
 int bgp_hodlr_shard_rows(const bgp_hodlr_t* h, int32_t s, int64_t* row0, int64_t* rows);
 int bgp_hodlr_finish_top(bgp_hodlr_t* h);
+/* NCCL communicator used INSIDE the ACA loop of a sharded compute: the candidate scan of the nodes above the shard cut
+ * is split across ranks by column chunk and the per-candidate maxima are MAX-all-reduced every iteration.  Rank 0 makes
+ * a unique id (128 bytes), the host broadcasts it (torch.distributed), every rank calls bgp_comm_init.  `nccl_path`
+ * may be NULL: the library already loaded in the process (torch's libnccl.so.2) is used.  Without a communicator a
+ * sharded compute recomputes the top-level scans redundantly on every rank. */
+int bgp_comm_unique_id(void* out128, const char* nccl_path);
+int bgp_comm_init(const void* id128, int rank, int world, const char* nccl_path);
+int bgp_comm_destroy(void);
+int bgp_comm_size(void);
 /* sharded solve: local part, then (host all-gathers the vector), then top part. */
 int bgp_hodlr_solve_local_dev(bgp_hodlr_t* h, double* b_dev, int64_t nrhs, int64_t ldb);
 int bgp_hodlr_solve_top_dev(bgp_hodlr_t* h, double* b_dev, int64_t nrhs, int64_t ldb);

@@ -173,3 +173,31 @@ def test_docs_golden_loglikelihood(gpu):
         gp = george.GP(kernel, solver=solver)
         gp.compute(x[:100], yerr[:100])
         assert abs(gp.log_likelihood(y[:100]) - 133.946394912) < 1e-6
+
+
+def test_exhaust_lowrank_matches_dense_mode(gpu, oracle):
+    """Matern-3/2 is exactly rank 2 on sorted 1-D inputs: most nodes run out of candidate rows.  The reference then
+    stores the block densely (hodlr.h:161-176, exhaust='dense'); exhaust='lowrank' keeps the verified factors.  Both must
+    give the reference's answer; the second must do it with rank <= 3 everywhere."""
+    from george_b200 import kernels as K
+    from george_b200.solvers._hodlr import HODLRSolver
+    from george_b200._spec import flatten
+    rng = np.random.default_rng(12)
+    n = 3000
+    x = np.sort(rng.uniform(0, 10 * n / 1000, n))[:, None]
+    yerr = 0.1 * np.ones(n)
+    y = np.sin(x[:, 0]) + 0.1 * rng.normal(size=n)
+    kernel = 1.0 * K.Matern32Kernel(1.0)
+    o = oracle.HODLR(flatten(kernel), x, yerr, min_size=100, tol=1e-10, seed=42, rng_mode=0)
+    assert any(nd["dense_fallback"] for nd in o.nodes())  # the hazard is real for the reference algorithm
+    res = {}
+    for mode in ("dense", "lowrank"):
+        s = HODLRSolver()
+        s.compute(kernel, x, yerr, min_size=100, tol=1e-10, seed=42, exhaust=mode)
+        res[mode] = (s.log_determinant, s.dot_solve(y), s.nodes())
+    for mode in res:
+        assert abs(res[mode][0] - o.log_determinant) <= 1e-10 * abs(o.log_determinant)
+        assert abs(res[mode][1] - o.dot_solve(y)) <= 1e-8 * abs(o.dot_solve(y))
+    assert max(nd["rank"] for nd in res["lowrank"][2]) <= 3
+    assert any(nd["dense_fallback"] for nd in res["lowrank"][2])   # the flag still reports the exhausted nodes
+    assert max(nd["rank"] for nd in res["dense"][2]) >= 100         # reference semantics: rank = min(rows, cols)
