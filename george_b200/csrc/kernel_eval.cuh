@@ -228,10 +228,16 @@ struct ScaledProfile1D {
     const double d = x1[0] - x2[0];
     const double r2 = d * d * m;
     double f;
-    if (SHAPE == BGP_SHAPE_EXPSQ) f = exp(-0.5 * r2);
-    else if (SHAPE == BGP_SHAPE_M32) { const double r = sqrt(3.0 * r2); f = (1.0 + r) * exp(-r); }
-    else if (SHAPE == BGP_SHAPE_M52) { const double r = sqrt(5.0 * r2); f = (1 + r + 5.0 * r2 / 3.0) * exp(-r); }
-    else f = exp(-sqrt(r2));
+    // exp(-t) rounds to exactly 0 in double for t > 745.14: far-apart pairs (the bulk of every large off-diagonal
+    // block) skip the software exp/sqrt; the branch is warp-uniform because a warp sweeps 32 neighbouring points.
+    if (SHAPE == BGP_SHAPE_EXPSQ) f = (r2 > 1490.4) ? 0.0 : exp(-0.5 * r2);
+    else if (SHAPE == BGP_SHAPE_M32) {
+      if (r2 > 185200.0) f = 0.0;  // sqrt(3 r2) > 745.3
+      else { const double r = sqrt(3.0 * r2); f = (1.0 + r) * exp(-r); }
+    } else if (SHAPE == BGP_SHAPE_M52) {
+      if (r2 > 111100.0) f = 0.0;  // sqrt(5 r2) > 745.3
+      else { const double r = sqrt(5.0 * r2); f = (1 + r + 5.0 * r2 / 3.0) * exp(-r); }
+    } else f = (r2 > 555400.0) ? 0.0 : exp(-sqrt(r2));  // sqrt(r2) > 745.2
     return c * f;
   }
 };
