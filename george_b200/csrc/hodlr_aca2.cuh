@@ -251,91 +251,66 @@ __global__ void __launch_bounds__(A2_THREADS) a2_init_kernel(A2Args a) {
 }
 
 // ---- eval: residual maxima of the pending candidate rows ------------------------------------------------------
+// Warp-autonomous: each warp owns 128 columns of the chunk (4 per lane, coalesced) and walks the candidate rows in
+// blocks of A2_CG with no block-level synchronisation and no shared memory: the candidate's coordinates and its U row
+// are warp-uniform (broadcast) loads, the arg-max is a shuffle reduction and one atomicMax per (candidate, warp).
 template <class KFn>
-__device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, int rank, int ncand, int ndim, KFn fn,
-                                             double (*s_x)[ACA_MAX_NDIM], double (*s_u)[128 + 1],
-                                             double (*s_red)[A2_THREADS / 32], int (*s_redi)[A2_THREADS / 32]) {
-  const int chunk = blockIdx.x;
-  const int lc = chunk - nd.cchunk0;
-  const int c_lo = lc * A2_CHUNK;
-  const int c_n = min(A2_CHUNK, nd.n_cols - c_lo);
+__device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, int rank, int ncand, int ndim, KFn fn) {
+  const int lc = blockIdx.x - nd.cchunk0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int w_lo = lc * A2_CHUNK + warp * (A2_CHUNK / (A2_THREADS / 32));  // first column of this warp
+  const int w_n = min(A2_CHUNK / (A2_THREADS / 32), nd.n_cols - w_lo);
+  if (w_n <= 0) return;
   const double* Vcols = a.Vp + (int64_t)nd.vcol * a.ld;
   const double* xr = a.x + (int64_t)nd.row0 * ndim;
-  const double* xc = a.x + (int64_t)(nd.col0 + c_lo) * ndim;
+  const double* xc = a.x + (int64_t)(nd.col0 + w_lo) * ndim;
   const int* cand = a.cand + nd.cand_off;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long* cmax = a.cmax + nd.cand_off;
+  int ncol[A2_EPT];
+#pragma unroll
+  for (int e = 0; e < A2_EPT; ++e) ncol[e] = min(lane + 32 * e, w_n - 1);  // clamped (masked in the arg-max)
 
   for (int cb = blockIdx.y * A2_CG; cb < ncand; cb += A2_GROUPS * A2_CG) {
     const int ncb = min(A2_CG, ncand - cb);
+    int row[A2_CG];
+#pragma unroll
+    for (int c = 0; c < A2_CG; ++c) row[c] = cand[cb + min(c, ncb - 1)];
     double vals[A2_CG][A2_EPT];
-    __syncthreads();
-    for (int t = threadIdx.x; t < A2_CG * ndim; t += A2_THREADS) {
-      const int c = t / ndim, q = t % ndim;
-      s_x[c][q] = xr[(int64_t)cand[cb + min(c, ncb - 1)] * ndim + q];  // pad with a repeat of the last candidate
-    }
-    __syncthreads();
 #pragma unroll
     for (int e = 0; e < A2_EPT; ++e) {
-      const int n = threadIdx.x + e * A2_THREADS;
-      const double* x2 = xc + (int64_t)min(n, c_n - 1) * ndim;
+      const double* x2 = xc + (int64_t)ncol[e] * ndim;
 #pragma unroll
-      for (int c = 0; c < A2_CG; ++c) vals[c][e] = fn(s_x[c], x2);
+      for (int c = 0; c < A2_CG; ++c) vals[c][e] = fn(xr + (int64_t)row[c] * ndim, x2);
     }
-    for (int k0 = 0; k0 < rank; k0 += 128) {
-      const int nk = min(128, rank - k0);
-      __syncthreads();
-      for (int t = threadIdx.x; t < A2_CG * nk; t += A2_THREADS) {
-        const int c = t / nk, k = t % nk;
-        s_u[c][k] = __ldcg(Vcols + (int64_t)(k0 + k) * a.ld + nd.row0 + cand[cb + min(c, ncb - 1)]);
-      }
-      __syncthreads();
-      for (int k = 0; k < nk; ++k) {
-        double vk[A2_EPT];
+    for (int k = 0; k < rank; ++k) {
+      const double* vcol = Vcols + (int64_t)k * a.ld;
+      double vk[A2_EPT], u[A2_CG];
 #pragma unroll
-        for (int e = 0; e < A2_EPT; ++e) {
-          const int n = threadIdx.x + e * A2_THREADS;
-          vk[e] = Vcols[(int64_t)(k0 + k) * a.ld + nd.col0 + c_lo + min(n, c_n - 1)];
-        }
+      for (int c = 0; c < A2_CG; ++c) u[c] = __ldcg(vcol + nd.row0 + row[c]);
 #pragma unroll
-        for (int c = 0; c < A2_CG; ++c) {
-          const double u = s_u[c][k];
+      for (int e = 0; e < A2_EPT; ++e) vk[e] = vcol[nd.col0 + w_lo + ncol[e]];
 #pragma unroll
-          for (int e = 0; e < A2_EPT; ++e) vals[c][e] -= u * vk[e];
-        }
-      }
+      for (int c = 0; c < A2_CG; ++c)
+#pragma unroll
+        for (int e = 0; e < A2_EPT; ++e) vals[c][e] -= u[c] * vk[e];
     }
-    // per-candidate arg-max over the chunk (lowest column on ties)
 #pragma unroll
     for (int c = 0; c < A2_CG; ++c) {
-      double best = -1.0, bval = 0.0;
-      int bidx = 0x7fffffff;
+      double best = 0.0;
+      bool isnan_any = false;
 #pragma unroll
       for (int e = 0; e < A2_EPT; ++e) {
-        const int n = threadIdx.x + e * A2_THREADS;
         const double av = fabs(vals[c][e]);
-        if (n < c_n && av > best) { best = av; bidx = c_lo + n; bval = vals[c][e]; }
+        if (lane + 32 * e < w_n) { best = fmax(best, av); isnan_any |= (av != av); }
       }
+      if (isnan_any) best = __longlong_as_double(0x7ff8000000000000ll);
+      unsigned long long bits = (unsigned long long)__double_as_longlong(best);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const double ov = __shfl_xor_sync(0xffffffffu, bval, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; bval = ov; }
+        const unsigned long long ob = __shfl_xor_sync(0xffffffffu, bits, o);
+        bits = ob > bits ? ob : bits;
       }
-      if (lane == 0) { s_red[c][warp] = bval; s_redi[c][warp] = bidx; }
-    }
-    __syncthreads();
-    if (threadIdx.x < ncb) {
-      const int c = threadIdx.x;
-      double bval = s_red[c][0];
-      int bidx = s_redi[c][0];
-      for (int w = 1; w < A2_THREADS / 32; ++w) {
-        const double ov = s_red[c][w];
-        const int oi = s_redi[c][w];
-        if (fabs(ov) > fabs(bval) || (fabs(ov) == fabs(bval) && oi < bidx)) { bval = ov; bidx = oi; }
-      }
-      (void)bidx;
-      atomicMax(a.cmax + nd.cand_off + cb + c, (unsigned long long)__double_as_longlong(fabs(bval)));
+      if (lane == 0 && c < ncb) atomicMax(cmax + cb + c, bits);
     }
   }
 }
@@ -344,10 +319,6 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
 template <int SHAPE>
 __global__ void __launch_bounds__(A2_THREADS, (SHAPE == BGP_SHAPE_GENERIC) ? 2 : 3) a2_eval_kernel(A2Args a) {
   __shared__ DevProgram P;
-  __shared__ double s_x[A2_CG][ACA_MAX_NDIM];
-  __shared__ double s_u[A2_CG][128 + 1];  // U(i, k) for a k-tile of 128
-  __shared__ double s_red[A2_CG][A2_THREADS / 32];
-  __shared__ int s_redi[A2_CG][A2_THREADS / 32];
   const int nid = a.cchunk_node[blockIdx.x];
   const A2State& st = a.states[nid];
   if (st.phase != A2_SELECT || !st.active) return;
@@ -356,16 +327,15 @@ __global__ void __launch_bounds__(A2_THREADS, (SHAPE == BGP_SHAPE_GENERIC) ? 2 :
   const A2Node nd = a.nodes[nid];
   // sharded run: the scan of a top node is dealt out by column chunk; the per-candidate maxima are all-reduced (MAX)
   if (nd.is_top && a.shard_count > 1 && ((int)(blockIdx.x - nd.cchunk0) % a.shard_count) != a.shard_rank) return;
-  stage_program(&P, a.prog);
   const int rank = st.rank;
-  __syncthreads();
-  const int ndim = P.ndim;
   if constexpr (SHAPE == BGP_SHAPE_GENERIC) {
+    stage_program(&P, a.prog);
+    __syncthreads();
     GenericKernelFn fn{&P};
-    a2_eval_body(a, nd, rank, ncand, ndim, fn, s_x, s_u, s_red, s_redi);
+    a2_eval_body(a, nd, rank, ncand, P.ndim, fn);
   } else {
-    ScaledProfile1D<SHAPE> fn{P.sc, P.sm};
-    a2_eval_body(a, nd, rank, ncand, 1, fn, s_x, s_u, s_red, s_redi);
+    ScaledProfile1D<SHAPE> fn{a.prog->sc, a.prog->sm};
+    a2_eval_body(a, nd, rank, ncand, 1, fn);
   }
 }
 inline void a2_eval_launch(int shape, dim3 grid, cudaStream_t s, const A2Args& a) {
