@@ -73,6 +73,8 @@ struct bgp_hodlr {
   DevBuf<A2EPart> d_epart;
   DevBuf<int> d_cand, d_cand_k, d_cand_words, d_cchunk_node, d_rchunk_node, d_nactive;
   DevBuf<unsigned long long> d_cmax, d_stats;
+  DevBuf<int4> d_work;
+  DevBuf<int> d_work_count;
   bool profile = false;
   std::vector<cudaEvent_t> prof_events;
   double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -203,6 +205,11 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   int n_top = 0;
   for (int i = 0; i < nn; ++i) n_top += hn[i].is_top;
   BGP_TRY(h->d_stats.reserve(4, s));
+  int64_t work_cap = 0;
+  for (int i = 0; i < nn; ++i) work_cap += (int64_t)hn[i].n_cchunks * ((hn[i].bmax + A2_CG * A2_ITEM_CB - 1) / (A2_CG * A2_ITEM_CB));
+  BGP_TRY(h->d_work.reserve((size_t)(2 * work_cap), s));
+  BGP_TRY(h->d_work_count.reserve(2, s));
+  BGP_CUDA(cudaMemsetAsync(h->d_work_count.p, 0, sizeof(int) * 2, s));
   BGP_CUDA(cudaMemsetAsync(h->d_stats.p, 0, sizeof(unsigned long long) * 4, s));
   BGP_CUDA(cudaMemcpyAsync(h->d_a2nodes.p, hn.data(), sizeof(A2Node) * nn, cudaMemcpyHostToDevice, s));
   BGP_CUDA(cudaMemcpyAsync(h->d_cchunk_node.p, cchunk_node.data(), sizeof(int) * ncc, cudaMemcpyHostToDevice, s));
@@ -215,6 +222,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   a.cand = h->d_cand.p; a.cand_k = h->d_cand_k.p; a.cand_words = h->d_cand_words.p; a.cmax = h->d_cmax.p; a.epart = h->d_epart.p;
   a.cchunk_node = h->d_cchunk_node.p; a.rchunk_node = h->d_rchunk_node.p; a.vpart = h->d_vpart.p; a.upart = h->d_upart.p;
   a.capmax = capmax; a.n_active = h->d_nactive.p; a.stats = h->d_stats.p;
+  a.work = h->d_work.p; a.work_count = h->d_work_count.p; a.work_cap = (int)work_cap; a.iter = -1;
   a.shard_rank = dist_top ? h->opts.shard_rank : 0; a.shard_count = dist_top ? h->opts.shard_count : 1;
   if (dist_top) BGP_CUDA(cudaMemcpyAsync(h->d_nactive.p + 1, &n_top, sizeof(int), cudaMemcpyHostToDevice, s));
   static bool a2_attr = false;
@@ -227,6 +235,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   a2_init_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), s>>>(a);
   BGP_LAUNCH_CHECK();
   int active = nn, iters = 0;
+  const int eval_grid = num_sms() * 6;  // persistent CTAs over the work list (2-3 resident per SM, a few rounds)
   bool top_active = dist_top && n_top > 0;  // identical on every rank: the top nodes take identical decisions
   while (active > 0) {
     for (int rep = 0; rep < 8; ++rep) {
@@ -238,7 +247,8 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
         }
         BGP_CUDA(cudaEventRecord(h->prof_events[2 * iters], s));
       }
-      a2_eval_launch(h->prog.shape, dim3(ncc, A2_GROUPS), s, a);
+      a.iter = iters;
+      a2_eval_launch(h->prog.shape, dim3(eval_grid), s, a);
       if (h->profile) BGP_CUDA(cudaEventRecord(h->prof_events[2 * iters + 1], s));
       if (top_active) BGP_TRY(comm_allreduce_max_u64(h->d_cmax.p, (size_t)top_cand_total, s));
       BGP_LAUNCH_CHECK();
@@ -632,7 +642,7 @@ void bgp_hodlr_destroy(bgp_hodlr_t* h) {
   h->d_ticket.release(); h->d_chain_done.release(); h->d_ncols_by_depth.release(); h->d_chain_state.release();
   h->d_a2nodes.release(); h->d_a2states.release(); h->d_epart.release(); h->d_cand.release(); h->d_cand_k.release();
   h->d_cand_words.release(); h->d_cchunk_node.release(); h->d_rchunk_node.release(); h->d_nactive.release();
-  h->d_vpart.release(); h->d_upart.release(); h->d_cmax.release(); h->d_stats.release();
+  h->d_vpart.release(); h->d_upart.release(); h->d_cmax.release(); h->d_stats.release(); h->d_work.release(); h->d_work_count.release();
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   if (h->sA) {
     cudaStreamSynchronize(h->sA); cudaStreamSynchronize(h->sB);

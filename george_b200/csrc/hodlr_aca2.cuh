@@ -21,7 +21,8 @@ constexpr int A2_CHUNK = 1024;    // rows / columns per work item
 constexpr int A2_THREADS = 256;
 constexpr int A2_EPT = A2_CHUNK / A2_THREADS;  // elements per thread
 constexpr int A2_CG = 4;          // candidates evaluated together (register blocking)
-constexpr int A2_GROUPS = 4;      // candidate groups (gridDim.y of the eval kernel)
+constexpr int A2_ITEM_CB = 8;      // candidate blocks (of A2_CG rows) per eval work item
+constexpr int A2_GROUPS = 16;     // candidate groups (gridDim.y of the eval kernel)
 constexpr int A2_BMAX = 2048;     // max speculative candidates per iteration
 constexpr int A2_HASH = 4096;     // open-addressing slots of the swap-pop overlay (>= 2 * A2_BMAX)
 
@@ -133,7 +134,8 @@ __device__ __forceinline__ int a2_hash_find(const int* hkey, int pos) {
 // cand[c] = row, cand_k[c] = position, words[c] = mt19937 words consumed up to and including draw c.
 __device__ inline void a2_generate(A2State& st, A2NodeSmem& S, int* __restrict__ index, int* __restrict__ cand,
                                    int* __restrict__ cand_k, int* __restrict__ words, int bmax,
-                                   unsigned long long* __restrict__ cmax) {
+                                   unsigned long long* __restrict__ cmax, const A2Node& nd, int nid, int4* work_next,
+                                   int* work_count_next, int work_cap, int shard_rank, int shard_count) {
   const int n_index = st.n_index;
   const int B = min(min(st.B, bmax), n_index);
   // Lemire's multiply-shift rejects with probability s / 2^32 per draw; draw B words in parallel assuming none does and
@@ -193,6 +195,24 @@ __device__ inline void a2_generate(A2State& st, A2NodeSmem& S, int* __restrict__
     const int h = a2_hash_find(S.hkey, S.k[c]);
     index[S.k[c]] = S.hval[h];  // final content of every touched position (duplicates write the same value)
   }
+  // publish the evaluation work of the NEXT eval launch: one item = (column chunk, A2_ITEM_CB candidate blocks).
+  // In a sharded run the chunks of a node above the cut are dealt round-robin to the ranks.
+  {
+    const int per_chunk = (B + A2_CG * A2_ITEM_CB - 1) / (A2_CG * A2_ITEM_CB);
+    int my_chunks = nd.n_cchunks;
+    const bool split = nd.is_top && shard_count > 1;
+    if (split) my_chunks = (nd.n_cchunks - shard_rank + shard_count - 1) / shard_count;
+    const int n_items = my_chunks * per_chunk;
+    if (threadIdx.x == 0) S.flag = atomicAdd(work_count_next, n_items);
+    __syncthreads();
+    const int base = S.flag;
+    for (int t = threadIdx.x; t < n_items; t += blockDim.x) {
+      const int ci = t / per_chunk, pi = t % per_chunk;
+      const int lc = split ? (shard_rank + ci * shard_count) : ci;
+      const int c0 = pi * A2_CG * A2_ITEM_CB;
+      if (base + t < work_cap) work_next[base + t] = make_int4(nd.cchunk0 + lc, c0, min(A2_CG * A2_ITEM_CB, B - c0), nid);
+    }
+  }
   __syncthreads();
 }
 
@@ -221,6 +241,10 @@ struct A2Args {
   double* upart;   // per row chunk
   int capmax;
   int* n_active;
+  int4* work;          // eval work items (chunk, first candidate, #candidates, node), two buffers of work_cap
+  int* work_count;     // [2] item counters (buffer i%2 is consumed by iteration i and refilled for i+2)
+  int work_cap;
+  int iter;            // lock-step iteration number (selects the buffers)
   int shard_rank, shard_count;  // multi-GPU: top nodes' column chunks are dealt round-robin to the ranks
   unsigned long long* stats;  // [0] candidate-row kernel evaluations, [1] residual-update FMAs, [2] candidates, [3] accepted
 };
@@ -247,7 +271,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_init_kernel(A2Args a) {
     return;
   }
   a2_generate(st, S, index, a.cand + nd.cand_off, a.cand_k + nd.cand_off, a.cand_words + nd.cand_off, nd.bmax,
-              a.cmax + nd.cand_off);
+              a.cmax + nd.cand_off, nd, nid, a.work, a.work_count, a.work_cap, a.shard_rank, a.shard_count);
 }
 
 // ---- eval: residual maxima of the pending candidate rows ------------------------------------------------------
@@ -255,8 +279,9 @@ __global__ void __launch_bounds__(A2_THREADS) a2_init_kernel(A2Args a) {
 // blocks of A2_CG with no block-level synchronisation and no shared memory: the candidate's coordinates and its U row
 // are warp-uniform (broadcast) loads, the arg-max is a shuffle reduction and one atomicMax per (candidate, warp).
 template <class KFn>
-__device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, int rank, int ncand, int ndim, KFn fn) {
-  const int lc = blockIdx.x - nd.cchunk0;
+__device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, int rank, int chunk, int c_first,
+                                             int c_count, int ndim, KFn fn) {
+  const int lc = chunk - nd.cchunk0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int w_lo = lc * A2_CHUNK + warp * (A2_CHUNK / (A2_THREADS / 32));  // first column of this warp
   const int w_n = min(A2_CHUNK / (A2_THREADS / 32), nd.n_cols - w_lo);
@@ -270,7 +295,8 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
 #pragma unroll
   for (int e = 0; e < A2_EPT; ++e) ncol[e] = min(lane + 32 * e, w_n - 1);  // clamped (masked in the arg-max)
 
-  for (int cb = blockIdx.y * A2_CG; cb < ncand; cb += A2_GROUPS * A2_CG) {
+  const int ncand = c_first + c_count;
+  for (int cb = c_first; cb < ncand; cb += A2_CG) {
     const int ncb = min(A2_CG, ncand - cb);
     int row[A2_CG];
 #pragma unroll
@@ -319,23 +345,27 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
 template <int SHAPE>
 __global__ void __launch_bounds__(A2_THREADS, (SHAPE == BGP_SHAPE_GENERIC) ? 2 : 3) a2_eval_kernel(A2Args a) {
   __shared__ DevProgram P;
-  const int nid = a.cchunk_node[blockIdx.x];
-  const A2State& st = a.states[nid];
-  if (st.phase != A2_SELECT || !st.active) return;
-  const int ncand = st.ncand;
-  if (ncand <= (int)blockIdx.y * A2_CG) return;
-  const A2Node nd = a.nodes[nid];
-  // sharded run: the scan of a top node is dealt out by column chunk; the per-candidate maxima are all-reduced (MAX)
-  if (nd.is_top && a.shard_count > 1 && ((int)(blockIdx.x - nd.cchunk0) % a.shard_count) != a.shard_rank) return;
-  const int rank = st.rank;
+  // persistent CTAs sweep the work list published by the node kernels of the previous step: perfectly balanced over
+  // the chip whatever mix of nodes is still active, and no empty CTAs
+  const int buf = a.iter & 1;
+  const int n_items = min(a.work_count[buf], a.work_cap);
+  const int4* items = a.work + (int64_t)buf * a.work_cap;
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.work_count[buf ^ 1] = 0;  // refilled by decide / finish of this iteration
   if constexpr (SHAPE == BGP_SHAPE_GENERIC) {
     stage_program(&P, a.prog);
     __syncthreads();
-    GenericKernelFn fn{&P};
-    a2_eval_body(a, nd, rank, ncand, P.ndim, fn);
-  } else {
-    ScaledProfile1D<SHAPE> fn{a.prog->sc, a.prog->sm};
-    a2_eval_body(a, nd, rank, ncand, 1, fn);
+  }
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int4 w = items[it];
+    const A2Node& nd = a.nodes[w.w];
+    const int rank = a.states[w.w].rank;
+    if constexpr (SHAPE == BGP_SHAPE_GENERIC) {
+      GenericKernelFn fn{&P};
+      a2_eval_body(a, nd, rank, w.x, w.y, w.z, P.ndim, fn);
+    } else {
+      ScaledProfile1D<SHAPE> fn{a.prog->sc, a.prog->sm};
+      a2_eval_body(a, nd, rank, w.x, w.y, w.z, 1, fn);
+    }
   }
 }
 inline void a2_eval_launch(int shape, dim3 grid, cudaStream_t s, const A2Args& a) {
@@ -416,7 +446,11 @@ __global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
   }
   __syncthreads();
   if (st.n_index == 0) return;
-  a2_generate(st, S, index, cand, cand_k, words, nd.bmax, a.cmax + nd.cand_off);
+  {
+    const int nb = (a.iter + 1) & 1;
+    a2_generate(st, S, index, cand, cand_k, words, nd.bmax, a.cmax + nd.cand_off, nd, nid, a.work + (int64_t)nb * a.work_cap,
+                a.work_count + nb, a.work_cap, a.shard_rank, a.shard_count);
+  }
 }
 
 // ---- vrow: residual of the winning row over one column chunk, stored UN-normalised in panel column `rank`, plus the
@@ -679,8 +713,12 @@ __global__ void __launch_bounds__(A2_THREADS) a2_finish_kernel(A2Args a) {
   }
   __syncthreads();
   if (s_done) return;
-  a2_generate(st, S, a.idx_ws + nd.idx_off, a.cand + nd.cand_off, a.cand_k + nd.cand_off, a.cand_words + nd.cand_off, nd.bmax,
-              a.cmax + nd.cand_off);
+  {
+    const int nb = (a.iter + 1) & 1;
+    a2_generate(st, S, a.idx_ws + nd.idx_off, a.cand + nd.cand_off, a.cand_k + nd.cand_off, a.cand_words + nd.cand_off, nd.bmax,
+                a.cmax + nd.cand_off, nd, nid, a.work + (int64_t)nb * a.work_cap, a.work_count + nb, a.work_cap, a.shard_rank,
+                a.shard_count);
+  }
 }
 
 // ---- dense fallback fill (hodlr.h:161-176): V = I, U = K(rows, cols) ---------------------------------------------
