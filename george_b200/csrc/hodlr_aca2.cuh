@@ -23,8 +23,8 @@ constexpr int A2_EPT = A2_CHUNK / A2_THREADS;  // elements per thread
 constexpr int A2_CG = 4;          // candidates evaluated together (register blocking)
 constexpr int A2_ITEM_CB = 8;      // candidate blocks (of A2_CG rows) per eval work item
 constexpr int A2_GROUPS = 16;     // candidate groups (gridDim.y of the eval kernel)
-constexpr int A2_BMAX = 2048;     // max speculative candidates per iteration
-constexpr int A2_HASH = 4096;     // open-addressing slots of the swap-pop overlay (>= 2 * A2_BMAX)
+constexpr int A2_BMAX = 4096;     // max speculative candidates per iteration
+constexpr int A2_HASH = 8192;     // open-addressing slots of the swap-pop overlay (>= 2 * A2_BMAX)
 
 struct A2Node {  // static description
   int row0, n_rows, col0, n_cols;
@@ -183,8 +183,7 @@ __device__ inline void a2_generate(A2State& st, A2NodeSmem& S, int* __restrict__
       S.ok[c] = val;  // becomes cand[c]
       const int hl = a2_hash_find(S.hkey, last);
       const int lastval = (S.hkey[hl] == last) ? S.hval[hl] : S.ol[c];
-      h = a2_hash_find(S.hkey, pos);
-      S.hkey[h] = pos;
+      S.hkey[h] = pos;  // slot h is still the right one: the look-up of `last` inserts nothing
       S.hval[h] = lastval;
     }
   }
