@@ -339,7 +339,7 @@ def run_ours(args):
         traffic = None
         try:
             import csv
-            with open(os.path.join(ROOT, "profiles", "prof_a2_eval_r01_v1_raw.csv")) as fh:
+            with open(os.path.join(ROOT, "profiles", "prof_a2_eval_r01_v3_raw.csv")) as fh:
                 rows = list(csv.reader(fh))
             hdr = rows[0]
             traffic = (float(rows[2][hdr.index("dram__bytes_read.sum")]) + float(rows[2][hdr.index("dram__bytes_write.sum")])) * 1e6

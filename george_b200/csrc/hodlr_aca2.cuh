@@ -175,16 +175,57 @@ __device__ inline void a2_generate(A2State& st, A2NodeSmem& S, int* __restrict__
     S.ol[c] = index[n_index - 1 - c];
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int c = 0; c < B; ++c) {
-      const int pos = S.k[c], last = n_index - 1 - c;
-      int h = a2_hash_find(S.hkey, pos);
-      const int val = (S.hkey[h] == pos) ? S.hval[h] : S.ok[c];
-      S.ok[c] = val;  // becomes cand[c]
-      const int hl = a2_hash_find(S.hkey, last);
-      const int lastval = (S.hkey[hl] == last) ? S.hval[hl] : S.ol[c];
-      S.hkey[h] = pos;  // slot h is still the right one: the look-up of `last` inserts nothing
-      S.hval[h] = lastval;
+  // Resolve the swap-pop chain.  Warp 0 takes the candidates 32 at a time: a group whose drawn positions are distinct and
+  // do not fall on the 32 "last" slots the group itself reads has no read-after-write dependence inside the group, so
+  // its look-ups and inserts run in parallel (writes of EARLIER groups are already in the overlay); the rare other
+  // groups are replayed one draw at a time by lane 0.  Same result as the sequential loop of hodlr.h:179-183.
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    for (int c0 = 0; c0 < B; c0 += 32) {
+      const int c = c0 + lane;
+      const bool valid = c < B;
+      const int pos = valid ? S.k[c] : (-2 - lane);
+      const int last = n_index - 1 - c;
+      const unsigned same = __match_any_sync(0xffffffffu, pos);
+      const bool dup = valid && (__popc(same) > 1);
+      const bool tail = valid && pos <= n_index - 1 - c0 && pos >= n_index - 1 - (c0 + 31);
+      const unsigned bad = __ballot_sync(0xffffffffu, dup || tail);
+      if (bad == 0u) {
+        int val = 0, lastval = 0;
+        if (valid) {
+          const int h = a2_hash_find(S.hkey, pos);
+          val = (S.hkey[h] == pos) ? S.hval[h] : S.ok[c];
+          const int hl = a2_hash_find(S.hkey, last);
+          lastval = (S.hkey[hl] == last) ? S.hval[hl] : S.ol[c];
+        }
+        __syncwarp();
+        if (valid) {
+          unsigned h = ((unsigned)pos * 2654435761u) & (A2_HASH - 1);
+          while (true) {
+            const int prev = atomicCAS(&S.hkey[h], -1, pos);
+            if (prev == -1 || prev == pos) break;
+            h = (h + 1) & (A2_HASH - 1);
+          }
+          S.hval[h] = lastval;
+          S.ok[c] = val;  // becomes cand[c]
+        }
+        __syncwarp();
+      } else {
+        if (lane == 0) {
+          const int cend = min(B, c0 + 32);
+          for (int cc = c0; cc < cend; ++cc) {
+            const int p2 = S.k[cc], l2 = n_index - 1 - cc;
+            const int h = a2_hash_find(S.hkey, p2);
+            const int val = (S.hkey[h] == p2) ? S.hval[h] : S.ok[cc];
+            S.ok[cc] = val;
+            const int hl = a2_hash_find(S.hkey, l2);
+            const int lastval = (S.hkey[hl] == l2) ? S.hval[hl] : S.ol[cc];
+            S.hkey[h] = p2;
+            S.hval[h] = lastval;
+          }
+        }
+        __syncwarp();
+      }
     }
   }
   __syncthreads();
