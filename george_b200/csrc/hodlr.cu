@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "hodlr_kernels.cuh"
 #include "hodlr_aca2.cuh"
+#include "hodlr_leaf.cuh"
 #include "kernel_eval.cuh"
 
 namespace bgp {
@@ -399,8 +400,17 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
   BGP_TRY(h->d_leaf_logdet.reserve(std::max(nl, 1), sA));
   if (nl) {
     BGP_CUDA(cudaMemcpyAsync(h->d_leaves.p, hleaves.data(), sizeof(LeafDesc) * nl, cudaMemcpyHostToDevice, sA));
-    leaf_build_factor_kernel<<<nl, LEAF_THREADS, 0, sA>>>(h->d_prog.p, h->d_x.p, h->d_diag.p, h->d_leaves.p, h->d_L.p,
-                                                          h->d_leaf_logdet.p);
+    if (h->max_leaf <= 768) {
+      const int ldp = lf_panel_ld(h->max_leaf);
+      const size_t smem = sizeof(double) * (size_t)LF_NB * ldp;
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(leaf_factor_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+      leaf_factor_dmma_kernel<<<nl, LF_THREADS, smem, sA>>>(h->d_prog.p, h->d_x.p, h->d_diag.p, h->d_leaves.p, h->d_L.p,
+                                                            h->d_leaf_logdet.p, ldp);
+    } else {
+      leaf_build_factor_kernel<<<nl, LEAF_THREADS, 0, sA>>>(h->d_prog.p, h->d_x.p, h->d_diag.p, h->d_leaves.p, h->d_L.p,
+                                                            h->d_leaf_logdet.p);
+    }
     BGP_LAUNCH_CHECK();
   }
   BGP_CUDA(cudaEventRecord(h->ev[1], sA));  // leaves done
