@@ -169,7 +169,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   if (nn == 0) return BGP_OK;
   std::vector<A2Node> hn(nn);
   std::vector<int> cchunk_node, rchunk_node;
-  int64_t cand_total = 0, epart_total = 0, top_cand_total = 0;
+  int64_t cand_total = 0, top_cand_total = 0;
   // distributed scan of the nodes above the shard cut (needs the in-loop communicator; descs list those nodes first)
   const bool dist_top = h->opts.shard_count > 1 && comm_ready() && comm_world() == h->opts.shard_count;
   int capmax = 1;
@@ -185,7 +185,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
     for (int c = 0; c < a.n_rchunks; ++c) rchunk_node.push_back(i);
     a.bmax = std::min(A2_BMAX, d.n_rows);
     a.cand_off = cand_total; cand_total += a.bmax;
-    a.epart_off = 0; a.is_top = (dist_top && h->nodes[d.pre_id].top) ? 1 : 0;
+    a.is_top = (dist_top && h->nodes[d.pre_id].top) ? 1 : 0;
     if (a.is_top) top_cand_total = cand_total;
     capmax = std::max(capmax, d.cap);
   }
@@ -196,7 +196,6 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   BGP_TRY(h->d_cand_k.reserve((size_t)cand_total, s));
   BGP_TRY(h->d_cand_words.reserve((size_t)cand_total, s));
   BGP_TRY(h->d_cmax.reserve((size_t)cand_total, s));
-  (void)epart_total;
   BGP_TRY(h->d_epart.reserve((size_t)std::max(ncc, 1), s));
   BGP_TRY(h->d_cchunk_node.reserve(ncc, s));
   BGP_TRY(h->d_rchunk_node.reserve(nrc, s));
@@ -770,7 +769,10 @@ int bgp_hodlr_node_pivots(const bgp_hodlr_t* hc, int64_t node, int32_t* rows, in
   bgp_hodlr_t* h = const_cast<bgp_hodlr_t*>(hc);
   if (!h || node < 0 || node >= (int64_t)h->nodes.size()) { set_error("node index out of range"); return BGP_ERR_INDEX; }
   const HNode& nd = h->nodes[node];
-  if (nd.is_leaf || h->piv_off[node] < 0 || nd.rank == 0 || nd.fallback) return BGP_OK;
+  // dense fallback nodes (exhaust_mode = dense) have no pivot list: their factors are the identity / the block itself
+  if (nd.is_leaf || h->piv_off[node] < 0 || nd.rank == 0 ||
+      (nd.fallback && h->opts.exhaust_mode == BGP_EXHAUST_DENSE))
+    return BGP_OK;
   BGP_CUDA(cudaMemcpy(rows, h->d_piv_rows.p + h->piv_off[node], sizeof(int) * nd.rank, cudaMemcpyDeviceToHost));
   BGP_CUDA(cudaMemcpy(cols, h->d_piv_cols.p + h->piv_off[node], sizeof(int) * nd.rank, cudaMemcpyDeviceToHost));
   return BGP_OK;

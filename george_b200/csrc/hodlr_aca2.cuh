@@ -10,7 +10,12 @@
 //     to the one-at-a-time loop.  B doubles after a fully rejected batch.  Kernels that are exactly low rank
 //     (Matern-3/2 in 1-D) reject EVERY row of most nodes; this turns that O(n_rows * n_cols) scan into a dense,
 //     perfectly parallel evaluation instead of n_rows dependent steps.
-//   * one iteration = 5 small launches shared by all nodes:  eval -> decide -> vnorm -> ucol -> finish.
+//   * one iteration = 6 small launches shared by all nodes:
+//       eval (persistent CTAs over a work list of (column chunk, candidate block) items; only per-candidate maxima
+//       leave the kernel, through atomicMax) -> decide (first usable candidate; RNG / row list committed to that draw)
+//       -> vrow (winning row's residual + chunk arg-max) -> pivot -> vnorm || ucol (one launch) -> finish (stopping
+//       rule, next candidates).  The host reads one "active nodes" counter every 8 iterations.
+//   * sharded runs split the scan of the nodes above the cut across ranks and MAX-all-reduce the maxima (comm.cu).
 #pragma once
 
 #include "hodlr_kernels.cuh"
@@ -22,7 +27,6 @@ constexpr int A2_THREADS = 256;
 constexpr int A2_EPT = A2_CHUNK / A2_THREADS;  // elements per thread
 constexpr int A2_CG = 4;          // candidates evaluated together (register blocking)
 constexpr int A2_ITEM_CB = 8;      // candidate blocks (of A2_CG rows) per eval work item
-constexpr int A2_GROUPS = 16;     // candidate groups (gridDim.y of the eval kernel)
 constexpr int A2_BMAX = 4096;     // max speculative candidates per iteration
 constexpr int A2_HASH = 8192;     // open-addressing slots of the swap-pop overlay (>= 2 * A2_BMAX)
 
@@ -31,7 +35,7 @@ struct A2Node {  // static description
   int vcol, cap, pre_id, node;
   int cchunk0, n_cchunks, rchunk0, n_rchunks;
   int bmax, is_top;  // is_top: node above the shard cut, its candidate scan is split across ranks by column chunk
-  int64_t idx_off, piv_off, cand_off, epart_off;
+  int64_t idx_off, piv_off, cand_off;
 };
 
 struct A2State {  // dynamic
@@ -274,7 +278,7 @@ struct A2Args {
   int* cand_k;     // drawn positions
   int* cand_words; // cumulative words
   unsigned long long* cmax;  // per candidate: bit pattern of max |residual| over all chunks (atomicMax)
-  A2EPart* epart;  // [epart_off + c * n_cchunks + chunk]
+  A2EPart* epart;  // one slot per column chunk: arg-max of the winning row's residual in that chunk
   const int* cchunk_node;  // chunk -> node
   const int* rchunk_node;
   double* vpart;   // per column chunk: [chunk * (capmax + 1)] : vn2 then dots[k]

@@ -63,3 +63,55 @@ def make_kernels():
         ("empty", K.EmptyKernel(ndim=2) + K.ConstantKernel(log_constant=0.1, ndim=2)),
     ]
     return zoo
+
+
+def reference_kernel_list():
+    """The kernel instances the reference's own suite exercises (tests/test_kernels.py:19-64 `kernels_to_test` and the
+    `test_stationary` variants :83-128), built from OUR classes."""
+    from george_b200 import kernels
+    out = [
+        kernels.ConstantKernel(log_constant=0.1),
+        kernels.ConstantKernel(log_constant=10.0, ndim=2),
+        kernels.ConstantKernel(log_constant=5.0, ndim=5),
+        kernels.DotProductKernel(),
+        kernels.DotProductKernel(ndim=2),
+        kernels.DotProductKernel(ndim=5, axes=0),
+        kernels.CosineKernel(log_period=1.0),
+        kernels.CosineKernel(log_period=0.5, ndim=2),
+        kernels.CosineKernel(log_period=0.5, ndim=2, axes=1),
+        kernels.CosineKernel(log_period=0.75, ndim=5, axes=[2, 3]),
+        kernels.ExpSine2Kernel(gamma=0.4, log_period=1.0),
+        kernels.ExpSine2Kernel(gamma=12., log_period=0.5, ndim=2),
+        kernels.ExpSine2Kernel(gamma=17., log_period=0.5, ndim=2, axes=1),
+        kernels.ExpSine2Kernel(gamma=13.7, log_period=-0.75, ndim=5, axes=[2, 3]),
+        kernels.ExpSine2Kernel(gamma=-0.7, log_period=0.75, ndim=5, axes=[2, 3]),
+        kernels.ExpSine2Kernel(gamma=-10, log_period=0.75),
+        kernels.LocalGaussianKernel(log_width=0.5, location=1.0),
+        kernels.LocalGaussianKernel(log_width=0.1, location=0.5, ndim=2),
+        kernels.LocalGaussianKernel(log_width=1.5, location=-0.5, ndim=2, axes=1),
+        kernels.LocalGaussianKernel(log_width=2.0, location=0.75, ndim=5, axes=[2, 3]),
+        kernels.LinearKernel(order=0, log_gamma2=0.0),
+        kernels.LinearKernel(order=2, log_gamma2=0.0),
+        kernels.LinearKernel(order=5, log_gamma2=1.0, ndim=2),
+        kernels.LinearKernel(order=3, log_gamma2=-1.0, ndim=5, axes=2),
+        kernels.LinearKernel(order=0, log_gamma2=0.0) + kernels.LinearKernel(order=1, log_gamma2=-1.0)
+        + kernels.LinearKernel(order=2, log_gamma2=-2.0),
+        kernels.PolynomialKernel(order=0, log_sigma2=-10.0),
+        kernels.PolynomialKernel(order=2, log_sigma2=-10.0),
+        kernels.PolynomialKernel(order=2, log_sigma2=0.0),
+        kernels.PolynomialKernel(order=5, log_sigma2=1.0, ndim=2),
+        kernels.PolynomialKernel(order=3, log_sigma2=-1.0, ndim=5, axes=2),
+        12. * kernels.ExpSine2Kernel(gamma=0.4, log_period=1.0, ndim=5),
+        12. * kernels.ExpSquaredKernel(0.4, ndim=3) + 0.1,
+    ]
+    stationary = [
+        (kernels.ExpKernel, {}), (kernels.ExpSquaredKernel, {}), (kernels.Matern32Kernel, {}),
+        (kernels.Matern52Kernel, {}), (kernels.RationalQuadraticKernel, dict(log_alpha=np.log(1.0))),
+        (kernels.RationalQuadraticKernel, dict(log_alpha=np.log(0.1))),
+        (kernels.RationalQuadraticKernel, dict(log_alpha=np.log(10.0))),
+    ]
+    for cls, kw in stationary:
+        out += [cls(metric=0.1, **kw), cls(metric=1.0, **kw), cls(metric=10.0, **kw),
+                cls(metric=[1.0, 0.1, 10.0], ndim=3, **kw), cls(metric=1.0, ndim=3, **kw),
+                cls(metric=1.0, ndim=3, axes=2, **kw), cls(metric=1.0, ndim=3, axes=2, block=(-0.1, 0.1), **kw)]
+    return out
