@@ -54,6 +54,8 @@ SIGNATURES = {
     "bgp_kmat_diagonal": (C.c_int, [_specp, _p, _p, _i64, _p]),
     "bgp_kmat_gradient_symmetric": (C.c_int, [_specp, _p, _p, _i64, _p]),
     "bgp_kmat_gradient_general": (C.c_int, [_specp, _p, _p, _i64, _p, _i64, _p]),
+    "bgp_kmat_x1_gradient_general": (C.c_int, [_specp, _p, _i64, _p, _i64, _p]),
+    "bgp_kmat_x2_gradient_general": (C.c_int, [_specp, _p, _i64, _p, _i64, _p]),
     "bgp_kmat_symmetric_dev": (C.c_int, [_specp, _p, _i64, _p, _p, _i64]),
     "bgp_kmat_general_dev": (C.c_int, [_specp, _p, _i64, _p, _i64, _p, _i64]),
     "bgp_dense_create": (C.c_int, [C.POINTER(_p)]),

@@ -363,6 +363,83 @@ __device__ inline double kernel_value_grad(const DevProgram& P, const double* x1
   return val[0];
 }
 
+// ---- gradients with respect to the input coordinates (kernel_interface.cpp:127-157); not on the hot path ----------
+// side 1: d k / d x1, side 2: d k / d x2.  Needs ndim <= BGP_MAX_DIM.
+__device__ inline double axis_x_gradient(const DevLeaf& L, int side, double x1, double x2) {
+  switch (L.kernel_type) {
+    case BGP_K_LINEAR:
+      if (L.p[1] == 0.0) return 0.0;
+      return (side == 1 ? x2 : x1) * L.p[1] * pow(x1 * x2, L.p[1] - 1.0) * L.rp[0];
+    case BGP_K_LOCAL_GAUSSIAN: {
+      const double d1 = x1 - L.p[0], d2 = x2 - L.p[0];
+      return -2.0 * exp(-(d1 * d1 + d2 * d2) * L.rp[0]) * (side == 1 ? d1 : d2) * L.rp[0];
+    }
+    case BGP_K_COSINE: return (side == 1 ? -L.rp[0] : L.rp[0]) * sin(L.rp[0] * (x1 - x2));
+    case BGP_K_EXP_SINE2: {
+      const double d = x1 - x2, s = sin(d * L.rp[0]);
+      const double g = exp(-L.p[0] * s * s) * L.rp[0] * L.p[0] * sin(2.0 * L.rp[0] * d);
+      return side == 1 ? -g : g;
+    }
+    case BGP_K_POLYNOMIAL:
+      if (L.p[1] == 0.0) return 0.0;
+      return (side == 1 ? x2 : x1) * L.p[1] * pow(x1 * x2 + L.rp[0], L.p[1] - 1.0);
+    case BGP_K_DOT_PRODUCT: return side == 1 ? x2 : x1;
+  }
+  return 0.0;
+}
+__device__ inline void leaf_x_gradient(const DevLeaf& L, int ndim, int side, const double* x1, const double* x2,
+                                       double* grad) {
+  for (int i = 0; i < ndim; ++i) grad[i] = 0.0;
+  if (L.metric_type != BGP_METRIC_NONE) {  // e.g. kernels.h:1953-2003
+    if (L.blocked && out_of_block(L, x1, x2)) return;
+    const double r2grad = 2.0 * radial_gradient(L, metric_r2(L, x1, x2));
+    if (L.metric_type == BGP_METRIC_ISOTROPIC) {        // metrics.h:93-99
+      for (int i = 0; i < L.naxes; ++i) { const int j = L.axes[i]; grad[j] = L.mvec[0] * (x1[j] - x2[j]); }
+    } else if (L.metric_type == BGP_METRIC_AXIS_ALIGNED) {  // metrics.h:133-138
+      for (int i = 0; i < L.naxes; ++i) { const int j = L.axes[i]; grad[j] = L.mvec[i] * (x1[j] - x2[j]); }
+    } else {                                              // metrics.h:233-246: forward substitution only
+      double r[BGP_MAX_DIM];
+      int k = 0;
+      for (int i = 0; i < L.naxes; ++i) {
+        double b = x1[L.axes[i]] - x2[L.axes[i]];
+        for (int j = 0; j < i; ++j, ++k) b -= L.mvec[k] * r[j];
+        b *= L.mvec[k++];
+        r[i] = b;
+      }
+      for (int i = 0; i < L.naxes; ++i) grad[L.axes[i]] = r[i];
+    }
+    for (int i = 0; i < ndim; ++i) grad[i] *= (side == 1 ? r2grad : -r2grad);
+    return;
+  }
+  for (int i = 0; i < L.naxes; ++i) { const int j = L.axes[i]; grad[j] = axis_x_gradient(L, side, x1[j], x2[j]); }
+}
+// Sum: kernels.h:94-108, Product: kernels.h:140-162
+__device__ inline void kernel_x_gradient(const DevProgram& P, int side, const double* x1, const double* x2, double* out) {
+  double g[BGP_STACK][BGP_MAX_DIM];
+  double val[BGP_STACK];
+  int sp = 0;
+  const int nd = P.ndim;
+  for (int i = 0; i < P.n_nodes; ++i) {
+    const int c = P.code[i];
+    if (c >= 0) {
+      leaf_x_gradient(P.leaf[c], nd, side, x1, x2, g[sp]);
+      val[sp] = leaf_value(P.leaf[c], x1, x2);
+      sp++;
+    } else {
+      sp--;
+      if (c == -1) {
+        for (int q = 0; q < nd; ++q) g[sp - 1][q] = g[sp - 1][q] + g[sp][q];
+        val[sp - 1] += val[sp];
+      } else {
+        const double k1 = val[sp - 1], k2 = val[sp];
+        for (int q = 0; q < nd; ++q) g[sp - 1][q] = k2 * g[sp - 1][q] + k1 * g[sp][q];
+        val[sp - 1] = k1 * k2;
+      }
+    }
+  }
+  for (int q = 0; q < nd; ++q) out[q] = g[0][q];
+}
+
 #endif  // __CUDACC__
 
 }  // namespace bgp

@@ -181,6 +181,25 @@ __global__ void __launch_bounds__(128) kmat_gradient_kernel(const DevProgram* __
   }
 }
 
+// input-coordinate gradient: out[(i*n2 + j)*ndim + q] = d k(x1_i, x2_j) / d x{side}_q  (kernel_interface.cpp:127-157)
+__global__ void __launch_bounds__(128) kmat_x_gradient_kernel(const DevProgram* __restrict__ gprog, int side,
+                                                              const double* __restrict__ x1, int64_t n1,
+                                                              const double* __restrict__ x2, int64_t n2,
+                                                              double* __restrict__ out) {
+  __shared__ DevProgram P;
+  stage_program(&P, gprog);
+  __syncthreads();
+  const int nd = P.ndim;
+  const int64_t total = n1 * n2;
+  double g[BGP_MAX_DIM];
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / n2, j = t - i * n2;
+    kernel_x_gradient(P, side, x1 + i * nd, x2 + j * nd, g);
+    double* o = out + t * nd;
+    for (int q = 0; q < nd; ++q) o[q] = g[q];
+  }
+}
+
 static size_t kmat_smem_general(int nd) {
   return ((sizeof(KmatSmem) + 15) & ~size_t(15)) + sizeof(double) * ((size_t)KM_TI * nd + 1 + (size_t)KM_TJ * nd + 1);
 }
@@ -296,7 +315,42 @@ static int kmat_grad_host(const bgp_kernel_spec_t* spec, const uint32_t* which, 
   return BGP_OK;
 }
 
+static int kmat_xgrad_host(const bgp_kernel_spec_t* spec, int side, const double* x1, int64_t n1, const double* x2,
+                           int64_t n2, double* out) {
+  BGP_TRY(require_device());
+  DevProgram P;
+  BGP_TRY(build_dev_program(spec, &P));
+  const int nd = P.ndim;
+  if (n1 < 0 || n2 < 0) { set_error("negative size"); return BGP_ERR_INVALID; }
+  if (n1 == 0 || n2 == 0) return BGP_OK;
+  cudaStream_t s = 0;
+  DevBuf<DevProgram> dprog;
+  DevBuf<double> dx1, dx2, dout;
+  BGP_TRY(upload_program(P, dprog, s));
+  BGP_TRY(dx1.alloc((size_t)n1 * nd, s));
+  BGP_CUDA(cudaMemcpyAsync(dx1.p, x1, sizeof(double) * n1 * nd, cudaMemcpyHostToDevice, s));
+  BGP_TRY(dx2.alloc((size_t)n2 * nd, s));
+  BGP_CUDA(cudaMemcpyAsync(dx2.p, x2, sizeof(double) * n2 * nd, cudaMemcpyHostToDevice, s));
+  const size_t nout = (size_t)n1 * n2 * nd;
+  BGP_TRY(dout.alloc(nout, s));
+  const int blocks = (int)std::min<int64_t>((n1 * n2 + 127) / 128, 16 * num_sms());
+  kmat_x_gradient_kernel<<<blocks, 128, 0, s>>>(dprog.p, side, dx1.p, n1, dx2.p, n2, dout.p);
+  BGP_LAUNCH_CHECK();
+  BGP_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, s));
+  BGP_CUDA(cudaStreamSynchronize(s));
+  return BGP_OK;
+}
+
 extern "C" {
+
+int bgp_kmat_x1_gradient_general(const bgp_kernel_spec_t* spec, const double* x1, int64_t n1, const double* x2,
+                                 int64_t n2, double* out) {
+  return kmat_xgrad_host(spec, 1, x1, n1, x2, n2, out);
+}
+int bgp_kmat_x2_gradient_general(const bgp_kernel_spec_t* spec, const double* x1, int64_t n1, const double* x2,
+                                 int64_t n2, double* out) {
+  return kmat_xgrad_host(spec, 2, x1, n1, x2, n2, out);
+}
 
 int bgp_kmat_symmetric(const bgp_kernel_spec_t* spec, const double* x, int64_t n, double* out) {
   return kmat_host(spec, x, n, x, n, out, 1);

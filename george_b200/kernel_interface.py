@@ -101,8 +101,16 @@ class KernelInterface(object):
                                                    _lib.ptr(out)))
         return out
 
+    def _x_gradient(self, fn, x1, x2):
+        x1, x2 = _as2d(x1, self.ndim), _as2d(x2, self.ndim)
+        out = np.empty((x1.shape[0], x2.shape[0], self.ndim), dtype=np.float64)
+        _lib.check(fn(C.byref(self._spec), _lib.ptr(x1), x1.shape[0], _lib.ptr(x2), x2.shape[0], _lib.ptr(out)))
+        return out
+
     def x1_gradient_general(self, x1, x2):
-        raise NotImplementedError("input-coordinate gradients are outside the accelerated path (SURVEY.md §8f)")
+        """d k(x1_i, x2_j) / d x1_i, shape (n1, n2, ndim) (reference kernel_interface.cpp:127-141)."""
+        return self._x_gradient(_lib.load().bgp_kmat_x1_gradient_general, x1, x2)
 
     def x2_gradient_general(self, x1, x2):
-        raise NotImplementedError("input-coordinate gradients are outside the accelerated path (SURVEY.md §8f)")
+        """d k(x1_i, x2_j) / d x2_j, shape (n1, n2, ndim) (reference kernel_interface.cpp:143-157)."""
+        return self._x_gradient(_lib.load().bgp_kmat_x2_gradient_general, x1, x2)

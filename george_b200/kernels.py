@@ -149,6 +149,34 @@ class Kernel(ModelSet):
                 "incorrect gradient for parameter '{0}' ({1})".format(self.get_parameter_names()[i], i)
 
 
+    def _test_x_gradient(self, side, x1, x2, eps, kwargs):
+        kwargs["atol"] = kwargs.get("atol", 0.5 * eps)
+        analytic = (self.get_x1_gradient if side == 1 else self.get_x2_gradient)(x1, x2=x2)
+        pts = [np.array(x1, dtype=np.float64), np.array(x1 if x2 is None else x2, dtype=np.float64)]
+        moved = pts[side - 1]
+        for i in range(len(moved)):
+            for k in range(self.ndim):
+                x0 = moved[i, k]
+                moved[i, k] = x0 + eps
+                plus = self.get_value(pts[0], x2=pts[1])
+                moved[i, k] = x0 - eps
+                minus = self.get_value(pts[0], x2=pts[1])
+                moved[i, k] = x0
+                fd = 0.5 * (plus - minus) / eps
+                if side == 1:
+                    assert np.allclose(analytic[i, :, k], fd[i], **kwargs)
+                else:
+                    assert np.allclose(analytic[:, i, k], fd[:, i], **kwargs)
+
+    def test_x1_gradient(self, x1, x2=None, eps=1.32e-6, **kwargs):
+        """Centred finite-difference check of d k / d x1 (reference kernels.py:166-182)."""
+        self._test_x_gradient(1, x1, x2, eps, kwargs)
+
+    def test_x2_gradient(self, x1, x2=None, eps=1.32e-6, **kwargs):
+        """Centred finite-difference check of d k / d x2 (reference kernels.py:184-200)."""
+        self._test_x_gradient(2, x1, x2, eps, kwargs)
+
+
 class _operator(Kernel):
     is_kernel = False
     kernel_type = -1

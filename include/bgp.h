@@ -124,6 +124,12 @@ int bgp_kmat_gradient_symmetric(const bgp_kernel_spec_t* spec, const uint32_t* w
                                 double* out /* n*n*n_params */);
 int bgp_kmat_gradient_general(const bgp_kernel_spec_t* spec, const uint32_t* which, const double* x1, int64_t n1,
                               const double* x2, int64_t n2, double* out /* n1*n2*n_params */);
+/* d k(x1_i, x2_j) / d x1_i  and  / d x2_j  — kernel_interface.cpp:127-141 (x1_gradient_general) and 143-157
+ * (x2_gradient_general).  out[(i*n2 + j)*ndim + q]. */
+int bgp_kmat_x1_gradient_general(const bgp_kernel_spec_t* spec, const double* x1, int64_t n1, const double* x2,
+                                 int64_t n2, double* out /* n1*n2*ndim */);
+int bgp_kmat_x2_gradient_general(const bgp_kernel_spec_t* spec, const double* x1, int64_t n1, const double* x2,
+                                 int64_t n2, double* out /* n1*n2*ndim */);
 /* device-resident build: out_dev[i*ld + j] (row-major, ld >= n2); diag_add_dev (may be NULL, symmetric only)
  * is added on the diagonal — the fusion of solvers/basic.py:64-65. */
 int bgp_kmat_symmetric_dev(const bgp_kernel_spec_t* spec, const double* x_dev, int64_t n, const double* diag_add_dev,

@@ -43,6 +43,7 @@ def lib():
             "oracle_value_symmetric": [vp, vp, i64, vp],
             "oracle_value_diagonal": [vp, vp, vp, i64, vp],
             "oracle_gradient_general": [vp, vp, vp, i64, vp, i64, vp],
+            "oracle_x_gradient_general": [vp, C.c_int, vp, i64, vp, i64, vp],
         }.items():
             getattr(L, name).restype = C.c_int
             getattr(L, name).argtypes = args
@@ -108,6 +109,14 @@ def gradient_general(spec, which, x1, x2):
     npar = lib().oracle_num_params(C.byref(spec))
     out = np.zeros((len(x1), len(x2), npar))
     assert lib().oracle_gradient_general(C.byref(spec), _p(which), _p(x1), len(x1), _p(x2), len(x2), _p(out)) == 0
+    return out
+
+
+def x_gradient_general(spec, side, x1, x2):
+    """side 1: d k / d x1, side 2: d k / d x2 -> (n1, n2, ndim)"""
+    x1, x2 = _c(x1), _c(x2)
+    out = np.zeros((len(x1), len(x2), x1.shape[1]))
+    assert lib().oracle_x_gradient_general(C.byref(spec), int(side), _p(x1), len(x1), _p(x2), len(x2), _p(out)) == 0
     return out
 
 

@@ -404,6 +404,16 @@ int oracle_gradient_general(const bgp_kernel_spec_t* spec, const uint32_t* which
   return 0;
 }
 
+// kernel_interface.cpp:127-157; side = 1 -> x1_gradient_general, side = 2 -> x2_gradient_general; out (n1, n2, ndim)
+int oracle_x_gradient_general(const bgp_kernel_spec_t* spec, int side, const double* x1, int64_t n1, const double* x2,
+                              int64_t n2, double* out) {
+  Program P; if (build_program(spec, &P)) return 1;
+  const int d = P.ndim;
+  for (int64_t i = 0; i < n1; ++i) for (int64_t j = 0; j < n2; ++j)
+    program_x_gradient(P, side, x1 + i * d, x2 + j * d, out + (i * n2 + j) * d);
+  return 0;
+}
+
 // _hodlr.cpp:55-94
 void* oracle_hodlr_compute(const bgp_kernel_spec_t* spec, const double* x, int64_t n, int32_t ndim, const double* yerr,
                            int32_t min_size, double tol, int32_t seed, int32_t rng_mode) {

@@ -26,6 +26,9 @@ def test_oracle_equals_reference_binary(oracle, kernel):
     if kernel.full_size:
         which = np.ones(kernel.full_size, dtype=np.uint32)
         assert np.array_equal(oracle.gradient_general(spec, which, t1, t1[:3]), r.gradient_general(which, t1, t1[:3]))
+    # input-coordinate gradients (kernel_interface.cpp:127-157)
+    assert np.array_equal(oracle.x_gradient_general(spec, 1, t1, t1[:3]), r.x1_gradient_general(t1, t1[:3]))
+    assert np.array_equal(oracle.x_gradient_general(spec, 2, t1[:3], t1), r.x2_gradient_general(t1[:3], t1))
 
 
 def test_stationary_constructor_errors():
@@ -51,3 +54,21 @@ def test_device_values_gradients_and_fd(gpu, oracle, kernel):
     if len(kernel):
         kernel.test_gradient(t1, eps=1.32e-6)
         kernel.test_gradient(t1, t1[:1], eps=1.32e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", KERNELS, ids=IDS)
+def test_device_x_gradients(gpu, oracle, kernel):
+    """reference tests/test_kernels.py:73-80 (test_x_gradient_kernel) on the CUDA path, plus device == oracle."""
+    from george_b200._spec import flatten
+    np.random.seed(123)
+    t1 = np.random.randn(20, kernel.ndim)
+    spec = flatten(kernel)
+    np.testing.assert_allclose(kernel.get_x1_gradient(t1, t1[:3]), oracle.x_gradient_general(spec, 1, t1, t1[:3]),
+                               rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(kernel.get_x2_gradient(t1[:3], t1), oracle.x_gradient_general(spec, 2, t1[:3], t1),
+                               rtol=1e-10, atol=1e-12)
+    kernel.test_x1_gradient(t1, eps=1.32e-6)
+    kernel.test_x1_gradient(t1, np.array(t1[:1]), eps=1.32e-6)
+    kernel.test_x2_gradient(t1, eps=1.32e-6)
+    kernel.test_x2_gradient(np.array(t1[:1]), t1, eps=1.32e-6)
