@@ -88,6 +88,8 @@ SIGNATURES = {
     "bgp_hodlr_last_work": (C.c_int, [_p, _dp]),
     "bgp_hodlr_set_profiling": (C.c_int, [_p, C.c_int]),
     "bgp_hodlr_last_aca_profile": (C.c_int, [_p, _dp]),
+    "bgp_selftest_lu": (C.c_int, [_i32, _i32, _p, _p, _p]),
+    "bgp_selftest_gemm": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _i32]),
     "bgp_hodlr_top_panel": (C.c_int, [_p, C.POINTER(_p), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
                                       C.POINTER(_i64)]),
     "bgp_hodlr_export_top": (C.c_int, [_p, _p, _i64]),

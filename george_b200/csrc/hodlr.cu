@@ -10,10 +10,12 @@
 // solve(): the same three kernels with the right-hand side as target (K7).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
 #include "hodlr_kernels.cuh"
+#include "hodlr_lu.cuh"
 #include "hodlr_aca2.cuh"
 #include "hodlr_leaf.cuh"
 #include "kernel_eval.cuh"
@@ -63,6 +65,12 @@ struct bgp_hodlr {
 
   DevBuf<DevProgram> d_prog;
   DevBuf<double> d_x, d_yerr, d_diag, d_L, d_leaf_logdet, d_node_logdet, d_V, d_U, d_S, d_W, d_scalar, d_rhs;
+  LuWorkspace lu_ws;                         // big-rank Woodbury step (hodlr_lu.cuh)
+  DevBuf<GemmDesc> d_gram_desc, d_upd_desc;
+  std::vector<NodeDesc> h_nodes;             // host copy of d_nodes
+  std::vector<int> cap_hint;                 // per-level ACA capacities the previous compute() ended with
+  int64_t cap_hint_n = -1;
+  int cap_hint_min_size = -1;
   DevBuf<LeafDesc> d_leaves;
   DevBuf<AcaDesc> d_aca;
   DevBuf<AcaOut> d_aca_out;
@@ -128,6 +136,11 @@ static int launch_leaf_solve(bgp_hodlr* h, double* X, int64_t ldx, const int* nc
 }
 
 // one internal level: W = V^T X (both halves), small solve, X -= U T.   factor: up-sweep (X = U panel) vs plain solve
+// Two paths: ranks whose 2r x 2r Woodbury matrix fits one CTA's shared memory (the common case) run three batched
+// kernels; larger ranks run the Gram / update products on DMMA and the blocked LU of hodlr_lu.cuh.
+static int launch_level_big(bgp_hodlr* h, const LevelInfo& L, double* X, int64_t ldx, int ncolsW, int own_off, int factor,
+                            int col_lo, int col_hi, cudaStream_t s);
+
 static int launch_level(bgp_hodlr* h, const LevelInfo& L, double* X, int64_t ldx, int ncolsW, int own_off, int factor,
                         int col_lo, int col_hi, cudaStream_t s) {
   const int nn = (int)L.nodes.size();
@@ -135,10 +148,14 @@ static int launch_level(bgp_hodlr* h, const LevelInfo& L, double* X, int64_t ldx
     return BGP_OK;
   }
   const int r = L.r;
-  const int64_t stride = (int64_t)r * ncolsW;
-  const size_t need = (size_t)nn * 2 * stride;
+  const int64_t stride = (int64_t)2 * r * ncolsW;  // one (2r x ncolsW) block per node
+  const size_t need = (size_t)nn * stride;
   if (need > h->w_cap) { set_error("internal: W workspace too small (%zu > %zu)", need, h->w_cap); return BGP_ERR_CUDA; }
   BGP_CUDA(cudaMemsetAsync(h->d_W.p, 0, sizeof(double) * need, s));
+  // diagnostics: BGP_SMALL_RANK_LIMIT=<2r> lowers the switch-over so the tests can drive every level through the big path
+  int small_limit = SS_MAX_N;
+  if (const char* e = getenv("BGP_SMALL_RANK_LIMIT")) small_limit = std::min(SS_MAX_N, atoi(e));
+  if (2 * r > small_limit) return launch_level_big(h, L, X, ldx, ncolsW, own_off, factor, col_lo, col_hi, s);
   const NodeDesc* nd = h->d_nodes.p + L.desc_off;
   const int max_nh = L.max_half + 1;
   {
@@ -148,17 +165,76 @@ static int launch_level(bgp_hodlr* h, const LevelInfo& L, double* X, int64_t ldx
   }
   {
     const size_t sbytes = sizeof(double) * (size_t)(2 * r) * (2 * r);
-    const int in_smem = sbytes <= 160 * 1024;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(small_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
-    small_solve_kernel<<<nn, SS_THREADS, in_smem ? sbytes : 0, s>>>(nd, h->d_W.p, stride, ncolsW, own_off, factor, h->d_S.p,
-                                                                    h->d_node_logdet.p, L.desc_off, in_smem);
+    small_solve_kernel<<<nn, SS_THREADS, sbytes, s>>>(nd, h->d_W.p, stride, ncolsW, own_off, factor, h->d_S.p,
+                                                      h->d_node_logdet.p, L.desc_off);
     BGP_LAUNCH_CHECK();
   }
   if (col_hi > col_lo) {
     dim3 grid((max_nh + UP_ROWS - 1) / UP_ROWS, nn * 2, (col_hi - col_lo + UP_TC - 1) / UP_TC);
     update_nn_kernel<<<grid, UP_THREADS, 0, s>>>(nd, h->d_U.p, h->n, X, ldx, col_lo, col_hi, h->d_W.p, stride, 0);
     BGP_LAUNCH_CHECK();
+  }
+  return BGP_OK;
+}
+
+static int launch_level_big(bgp_hodlr* h, const LevelInfo& L, double* X, int64_t ldx, int ncolsW, int own_off, int factor,
+                            int col_lo, int col_hi, cudaStream_t s) {
+  const int nn = (int)L.nodes.size();
+  const int r = L.r, n2 = 2 * r;
+  const int64_t stride = (int64_t)n2 * ncolsW;
+  const int64_t ldv = h->n, ldu = h->n;
+  double* W = h->d_W.p;
+  constexpr int KCHUNK = 4096;  // rows per split-K slice of the Gram product
+  std::vector<LuNode> lun(nn);
+  std::vector<GemmDesc> gram, upd;
+  int max_nh = 0;
+  for (int b = 0; b < nn; ++b) {
+    const HNode& nd = h->nodes[L.nodes[b]];
+    const int64_t s_off = h->h_nodes[L.desc_off + b].s_off;
+    lun[b].S = h->d_S.p + s_off;
+    lun[b].piv = reinterpret_cast<int*>(lun[b].S + (int64_t)n2 * n2);
+    lun[b].logdet = h->d_node_logdet.p + L.desc_off + b;
+    double* Wn = W + (int64_t)b * stride;
+    for (int hh = 0; hh < 2; ++hh) {
+      const int rs = nd.start + (hh ? nd.half : 0), nh = hh ? (nd.size - nd.half) : nd.half;
+      max_nh = std::max(max_nh, nh);
+      for (int k0 = 0; k0 < nh; k0 += KCHUNK) {  // W_h (r x ncolsW) += V_h^T X_h
+        GemmDesc g;
+        g.A = h->d_V.p + (int64_t)L.vcol * ldv + rs + k0; g.lda = ldv;   // A'(q, i) = V[i + q ldv]
+        g.B = X + rs + k0; g.ldb = ldx;                                   // B'(i, c) = X[i + c ldx]
+        g.C = Wn + (hh ? 0 : r); g.ldc = n2;
+        g.M = r; g.N = ncolsW; g.K = std::min(KCHUNK, nh - k0); g.mode = GD_ATOMIC_ADD;
+        gram.push_back(g);
+      }
+      if (col_hi > col_lo) {  // X_h[:, col_lo:col_hi] -= U_h T_h
+        GemmDesc g;
+        g.A = h->d_U.p + (int64_t)L.ucol * ldu + rs; g.lda = ldu;        // A'(i, q) = U[i + q ldu]
+        g.B = Wn + (hh ? r : 0) + (int64_t)col_lo * n2; g.ldb = n2;       // B'(q, c) = T[q + c 2r]
+        g.C = X + rs + (int64_t)col_lo * ldx; g.ldc = ldx;
+        g.M = nh; g.N = col_hi - col_lo; g.K = r; g.mode = GD_SUB;
+        upd.push_back(g);
+      }
+    }
+  }
+  BGP_TRY(lu_upload(h->d_gram_desc, gram, s));
+  BGP_TRY((gemm_dmma_launch<true, true>(h->d_gram_desc.p, (int)gram.size(), r, ncolsW, nullptr, s)));
+  if (factor) {
+    BGP_TRY(lu_upload(h->lu_ws.d_nodes, lun, s));
+    dim3 grid((unsigned)std::min<int64_t>(((int64_t)n2 * n2 + 255) / 256, 4096), nn);
+    lu_assemble_kernel<<<grid, 256, 0, s>>>(h->lu_ws.d_nodes.p, W, stride, r, own_off);
+    BGP_LAUNCH_CHECK();
+    BGP_TRY(lu_factor_batch(h->lu_ws, lun, n2, s));
+    // the own columns [own_off, own_off + r) only feed S; the targets are the ancestor columns [col_lo, col_hi)
+    if (col_hi > col_lo)
+      BGP_TRY(lu_solve_batch(h->lu_ws, lun, n2, W + (int64_t)col_lo * n2, stride, n2, col_hi - col_lo, false, s));
+  } else {
+    BGP_TRY(lu_solve_batch(h->lu_ws, lun, n2, W, stride, n2, ncolsW, true, s));
+  }
+  if (!upd.empty()) {
+    BGP_TRY(lu_upload(h->d_upd_desc, upd, s));
+    BGP_TRY((gemm_dmma_launch<false, true>(h->d_upd_desc.p, (int)upd.size(), max_nh, col_hi - col_lo, nullptr, s)));
   }
   return BGP_OK;
 }
@@ -372,6 +448,10 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
     L.max_cap = std::max(1, mh);
     L.cap = std::min(rcap0, L.max_cap);
   }
+  // a handle that already factored a tree of this shape starts from the capacities that run ended with (hyper-parameter
+  // loops call compute() repeatedly on the same x): no repeated ACA stage in the steady state
+  if (o.rank_capacity <= 0 && h->cap_hint_n == n && h->cap_hint_min_size == o.min_size && (int)h->cap_hint.size() == nlev)
+    for (int l = 0; l < nlev; ++l) h->levels[l].cap = std::min(h->levels[l].max_cap, std::max(h->levels[l].cap, h->cap_hint[l]));
 
   // ---- inputs ----
   BGP_TRY(upload_program(h->prog, h->d_prog, sA));
@@ -500,7 +580,12 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
         overflow = true;
       }
     }
-    if (!overflow) break;
+    if (!overflow) {
+      h->cap_hint.assign(nlev, 0);
+      for (int l = 0; l < nlev; ++l) h->cap_hint[l] = h->levels[l].cap;
+      h->cap_hint_n = n; h->cap_hint_min_size = o.min_size;
+      break;
+    }
     for (auto& L : h->levels) if (L.grow > L.cap) L.cap = L.grow;
     if (attempt > 16) { set_error("ACA capacity growth did not converge"); return BGP_ERR_RANK_CAPACITY; }
   }
@@ -544,6 +629,7 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
   BGP_CUDA(cudaMemcpyAsync(h->d_ncols_by_depth.p, ncols_by_depth.data(), sizeof(int) * ncols_by_depth.size(), cudaMemcpyHostToDevice, sA));
   if (ndesc) {
     BGP_CUDA(cudaMemcpyAsync(h->d_nodes.p, hnd.data(), sizeof(NodeDesc) * ndesc, cudaMemcpyHostToDevice, sA));
+    h->h_nodes = hnd;
     BGP_CUDA(cudaMemsetAsync(h->d_node_logdet.p, 0, sizeof(double) * ndesc, sA));
     int rmax = 0;
     for (auto& L : h->levels) rmax = std::max(rmax, L.r);
@@ -648,6 +734,7 @@ void bgp_hodlr_destroy(bgp_hodlr_t* h) {
   h->d_leaf_logdet.release(); h->d_node_logdet.release(); h->d_V.release(); h->d_U.release(); h->d_S.release();
   h->d_W.release(); h->d_scalar.release(); h->d_rhs.release(); h->d_leaves.release(); h->d_aca.release();
   h->d_aca_out.release(); h->d_nodes.release(); h->d_idx.release(); h->d_piv_rows.release(); h->d_piv_cols.release();
+  h->lu_ws.d_nodes.release(); h->lu_ws.d_trsm.release(); h->lu_ws.d_gemm.release(); h->d_gram_desc.release(); h->d_upd_desc.release();
   h->d_ticket.release(); h->d_chain_done.release(); h->d_ncols_by_depth.release(); h->d_chain_state.release();
   h->d_a2nodes.release(); h->d_a2states.release(); h->d_epart.release(); h->d_cand.release(); h->d_cand_k.release();
   h->d_cand_words.release(); h->d_cchunk_node.release(); h->d_rchunk_node.release(); h->d_nactive.release();
@@ -796,6 +883,52 @@ int bgp_hodlr_last_aca_profile(const bgp_hodlr_t* h, double* p5) {
 int bgp_hodlr_last_work(const bgp_hodlr_t* h, double* w6) {
   if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
   for (int i = 0; i < 6; ++i) w6[i] = h->work[i];
+  return BGP_OK;
+}
+
+// ---- diagnostics: the dense building blocks of the big-rank path, callable on their own (tests/test_gpu_linalg.py) ----
+int bgp_selftest_lu(int32_t n, int32_t nrhs, const double* S_host, double* R_host, double* logdet) {
+  BGP_TRY(require_device());
+  if (n <= 0 || nrhs < 0) { set_error("bgp_selftest_lu: bad sizes"); return BGP_ERR_INVALID; }
+  cudaStream_t s = 0;
+  DevBuf<double> dS, dR, dld;
+  LuWorkspace ws;
+  BGP_TRY(dS.alloc((size_t)n * n + n, s));
+  BGP_TRY(dR.alloc(std::max<size_t>((size_t)n * nrhs, 1), s));
+  BGP_TRY(dld.alloc(1, s));
+  BGP_CUDA(cudaMemcpyAsync(dS.p, S_host, sizeof(double) * n * n, cudaMemcpyHostToDevice, s));
+  if (nrhs) BGP_CUDA(cudaMemcpyAsync(dR.p, R_host, sizeof(double) * n * nrhs, cudaMemcpyHostToDevice, s));
+  std::vector<LuNode> nodes(1);
+  nodes[0].S = dS.p; nodes[0].piv = reinterpret_cast<int*>(dS.p + (size_t)n * n); nodes[0].logdet = dld.p;
+  BGP_TRY(lu_factor_batch(ws, nodes, n, s));
+  BGP_TRY(lu_solve_batch(ws, nodes, n, dR.p, 0, n, nrhs, false, s));
+  if (nrhs) BGP_CUDA(cudaMemcpyAsync(R_host, dR.p, sizeof(double) * n * nrhs, cudaMemcpyDeviceToHost, s));
+  BGP_CUDA(cudaMemcpyAsync(logdet, dld.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+  BGP_CUDA(cudaStreamSynchronize(s));
+  return BGP_OK;
+}
+
+int bgp_selftest_gemm(int32_t a_kcontig, int32_t b_kcontig, int32_t m, int32_t n, int32_t k, const double* A_host,
+                      int64_t lda, const double* B_host, int64_t ldb, double* C_host, int64_t ldc, int32_t atomic_add) {
+  BGP_TRY(require_device());
+  if (m <= 0 || n <= 0 || k <= 0) { set_error("bgp_selftest_gemm: bad sizes"); return BGP_ERR_INVALID; }
+  cudaStream_t s = 0;
+  const size_t na = (size_t)(a_kcontig ? m : k) * lda, nb = (size_t)(b_kcontig ? n : k) * ldb, nc = (size_t)n * ldc;
+  DevBuf<double> dA, dB, dC;
+  DevBuf<GemmDesc> dd;
+  BGP_TRY(dA.alloc(na, s)); BGP_TRY(dB.alloc(nb, s)); BGP_TRY(dC.alloc(nc, s)); BGP_TRY(dd.alloc(1, s));
+  BGP_CUDA(cudaMemcpyAsync(dA.p, A_host, sizeof(double) * na, cudaMemcpyHostToDevice, s));
+  BGP_CUDA(cudaMemcpyAsync(dB.p, B_host, sizeof(double) * nb, cudaMemcpyHostToDevice, s));
+  BGP_CUDA(cudaMemcpyAsync(dC.p, C_host, sizeof(double) * nc, cudaMemcpyHostToDevice, s));
+  GemmDesc g;
+  g.A = dA.p; g.B = dB.p; g.C = dC.p; g.M = m; g.N = n; g.K = k; g.mode = atomic_add ? GD_ATOMIC_ADD : GD_SUB;
+  g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+  BGP_CUDA(cudaMemcpyAsync(dd.p, &g, sizeof(g), cudaMemcpyHostToDevice, s));
+  if (a_kcontig && b_kcontig) BGP_TRY((gemm_dmma_launch<true, true>(dd.p, 1, m, n, nullptr, s)));
+  else if (!a_kcontig && b_kcontig) BGP_TRY((gemm_dmma_launch<false, true>(dd.p, 1, m, n, nullptr, s)));
+  else { set_error("bgp_selftest_gemm: only the (A K-contiguous | M-contiguous) x (B K-contiguous) variants are built here"); return BGP_ERR_INVALID; }
+  BGP_CUDA(cudaMemcpyAsync(C_host, dC.p, sizeof(double) * nc, cudaMemcpyDeviceToHost, s));
+  BGP_CUDA(cudaStreamSynchronize(s));
   return BGP_OK;
 }
 

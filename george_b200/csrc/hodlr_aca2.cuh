@@ -532,6 +532,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_vrow_kernel(A2Args a) {
     __syncthreads();
     for (int k = threadIdx.x; k < nk; k += A2_THREADS) s_u[k] = __ldcg(Vcols + (int64_t)(k0 + k) * a.ld + nd.row0 + i);
     __syncthreads();
+#pragma unroll 4
     for (int k = 0; k < nk; ++k) {
       const double u = s_u[k];
 #pragma unroll
@@ -671,6 +672,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_vnorm_ucol_kernel(A2Args a, int
     // V(j, k) for k < rank: columns already normalised in earlier iterations
     for (int k = threadIdx.x; k < nk; k += A2_THREADS) s_vr[k] = __ldcg(Vcols + (int64_t)(k0 + k) * a.ld + nd.col0 + j);
     __syncthreads();
+#pragma unroll 4
     for (int k = 0; k < nk; ++k) {
       const double v = s_vr[k];
 #pragma unroll

@@ -540,7 +540,9 @@ __global__ void finalize_panels_kernel(const NodeDesc* __restrict__ nodes, doubl
 // K6a: batched tall-skinny "TN" product   W_h = V_h^T * X_h   for both halves h of every node of a level
 //   V_h : rows of half h, the level's r columns of the V panel            (n_h x r)
 //   X_h : rows of half h, columns [0, ncols) of X (the U panel or a RHS)  (n_h x ncols)
-//   W_h : r x ncols, column-major (ld r), accumulated with atomics over row chunks
+//   W_h : r x ncols, accumulated with atomics over row chunks.  The two halves of a node share one (2r x ncols)
+//         column-major block (ld 2r): rows [0, r) = W_1 = V_1^T X_2, rows [r, 2r) = W_0 = V_0^T X_1 — the right-hand
+//         side [W_1; W_0] of the node's Woodbury system, stored the way the LU solve wants it.
 // hodlr.h:231-232 (Gram blocks of S) and :248-249 (V^T x) in one pass.
 // grid = (row chunk, node*2 + h, column tile)
 // ---------------------------------------------------------------------------------------------------------------
@@ -553,7 +555,7 @@ constexpr int GT_CHUNK = 2048;  // rows per CTA
 __global__ void __launch_bounds__(GT_THREADS) gram_tn_kernel(const NodeDesc* __restrict__ nodes,
                                                              const double* __restrict__ Vp, int64_t ldv,
                                                              const double* __restrict__ X, int64_t ldx, int ncols,
-                                                             double* __restrict__ W, int64_t w_stride_half) {
+                                                             double* __restrict__ W, int64_t w_stride_node) {
   __shared__ double sv[GT_ROWS][GT_TQ + 1];
   __shared__ double sx[GT_ROWS][GT_TC + 1];
   const NodeDesc nd = nodes[blockIdx.y >> 1];
@@ -566,7 +568,8 @@ __global__ void __launch_bounds__(GT_THREADS) gram_tn_kernel(const NodeDesc* __r
   if (c0 >= ncols) return;
   const int nc = min(GT_TC, ncols - c0);
   const int r = nd.r;
-  double* Wh = W + (int64_t)blockIdx.y * w_stride_half;  // r x ncols (node*2 + h blocks of w_stride_half)
+  double* Wh = W + (int64_t)(blockIdx.y >> 1) * w_stride_node + (h ? 0 : r);  // rows of half h in the node's 2r x ncols block
+  const int ldw = 2 * r;
 
   const int tq = threadIdx.x & 31, tc = threadIdx.x >> 5;  // thread -> (q = tq, c = tc + 8*e), e = 0..3
   for (int q0 = 0; q0 < r; q0 += GT_TQ) {
@@ -595,7 +598,7 @@ __global__ void __launch_bounds__(GT_THREADS) gram_tn_kernel(const NodeDesc* __r
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int c = tc + 8 * e;
-        if (c < nc) atomicAdd(Wh + (int64_t)(c0 + c) * r + q0 + tq, acc[e]);
+        if (c < nc) atomicAdd(Wh + (int64_t)(c0 + c) * ldw + q0 + tq, acc[e]);
       }
     }
   }
@@ -607,16 +610,16 @@ __global__ void __launch_bounds__(GT_THREADS) gram_tn_kernel(const NodeDesc* __r
 //                pivoting; same determinant / solution up to rounding), log|det| -> node_logdet, LU stored.
 //   then T = S^-1 [W_1[:, cols] ; W_0[:, cols]] for the `ncols - own` target columns, written back over W
 //   (T_top -> W_1, T_bot -> W_0 so the update kernel reads half h's coefficients from W_{1-h}... see update_nn_kernel).
-// One CTA per node; S lives in shared memory when it fits, else in the node's global S block.
+// One CTA per node, S in shared memory: the path for 2r <= SS_MAX_N; larger ranks go through hodlr_lu.cuh.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SS_THREADS = 256;
+constexpr int SS_MAX_N = 142;  // 142^2 doubles = 157.5 KB of dynamic shared memory
 
 __global__ void __launch_bounds__(SS_THREADS) small_solve_kernel(const NodeDesc* __restrict__ nodes,
-                                                                 double* __restrict__ W, int64_t w_stride_half,
+                                                                 double* __restrict__ W, int64_t w_stride_node,
                                                                  int ncols, int own_off, int factor,
                                                                  double* __restrict__ Sbuf,
-                                                                 double* __restrict__ node_logdet, int node_base,
-                                                                 int s_in_smem) {
+                                                                 double* __restrict__ node_logdet, int node_base) {
   extern __shared__ double ss_smem[];
   __shared__ double red[32];
   __shared__ int redi[32];
@@ -624,18 +627,18 @@ __global__ void __launch_bounds__(SS_THREADS) small_solve_kernel(const NodeDesc*
   const NodeDesc nd = nodes[blockIdx.x];
   const int r = nd.r, n2 = 2 * r;
   if (r == 0) { if (factor && threadIdx.x == 0) node_logdet[node_base + blockIdx.x] = 0.0; return; }
-  double* W0 = W + (int64_t)blockIdx.x * 2 * w_stride_half;  // half 0: V0^T X1  (r x ncols)
-  double* W1 = W0 + w_stride_half;                             // half 1: V1^T X2
+  double* W1 = W + (int64_t)blockIdx.x * w_stride_node;  // half 1: V1^T X2  (rows [0, r) of the 2r x ncols block)
+  double* W0 = W1 + r;                                    // half 0: V0^T X1  (rows [r, 2r))
   double* Sg = Sbuf + nd.s_off;                // n2 x n2 LU, column-major
   int* piv = reinterpret_cast<int*>(Sg + (int64_t)n2 * n2);
-  double* S = s_in_smem ? ss_smem : Sg;
+  double* S = ss_smem;
 
   if (factor) {
     for (int t = threadIdx.x; t < n2 * n2; t += SS_THREADS) {
       const int i = t % n2, j = t / n2;
       double v = (i == j) ? 1.0 : 0.0;
-      if (i < r && j >= r) v = W1[(int64_t)(own_off + j - r) * r + i];        // S(0:r, r:2r) = V1^T U1
-      else if (i >= r && j < r) v = W0[(int64_t)(own_off + j) * r + (i - r)];  // S(r:2r, 0:r) = V0^T U0
+      if (i < r && j >= r) v = W1[(int64_t)(own_off + j - r) * n2 + i];        // S(0:r, r:2r) = V1^T U1
+      else if (i >= r && j < r) v = W0[(int64_t)(own_off + j) * n2 + (i - r)];  // S(r:2r, 0:r) = V0^T U0
       S[(int64_t)j * n2 + i] = v;
     }
     __syncthreads();
@@ -674,11 +677,9 @@ __global__ void __launch_bounds__(SS_THREADS) small_solve_kernel(const NodeDesc*
       __syncthreads();
     }
     if (threadIdx.x == 0) node_logdet[node_base + blockIdx.x] = logdet;
-    if (s_in_smem) {
-      for (int t = threadIdx.x; t < n2 * n2; t += SS_THREADS) Sg[t] = S[t];
-    }
+    for (int t = threadIdx.x; t < n2 * n2; t += SS_THREADS) Sg[t] = S[t];
     __syncthreads();
-  } else if (s_in_smem) {
+  } else {
     for (int t = threadIdx.x; t < n2 * n2; t += SS_THREADS) S[t] = Sg[t];
     __syncthreads();
   }
@@ -686,9 +687,8 @@ __global__ void __launch_bounds__(SS_THREADS) small_solve_kernel(const NodeDesc*
   // solve for the target columns: one thread per column; rhs = [W1[:, c]; W0[:, c]] (hodlr.h:248-250)
   for (int c = threadIdx.x; c < ncols; c += SS_THREADS) {
     if (factor && c >= own_off && c < own_off + r) continue;  // own columns only feed S
-    double* t1 = W1 + (int64_t)c * r;
-    double* t0 = W0 + (int64_t)c * r;
-    auto get = [&](int i) -> double& { return i < r ? t1[i] : t0[i - r]; };
+    double* tc = W1 + (int64_t)c * n2;  // the column's 2r entries are contiguous: [W_1(:, c); W_0(:, c)]
+    auto get = [&](int i) -> double& { return tc[i]; };
     for (int k = 0; k < n2; ++k) {
       const int p = piv[k];
       if (p != k) { const double a = get(k); get(k) = get(p); get(p) = a; }
@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(SS_THREADS) small_solve_kernel(const NodeDesc*
 
 // ---------------------------------------------------------------------------------------------------------------
 // K6c: batched "NN" update   X_1 -= U_0 * T[0:r],  X_2 -= U_1 * T[r:2r]      (hodlr.h:252-253)
-// After small_solve_kernel, T[0:r] sits in W_1 and T[r:2r] in W_0, so half h reads its coefficients from W_{1-h}.
+// After the solve, T[0:r] sits in rows [0, r) of the node's block and T[r:2r] in rows [r, 2r): half h reads rows h*r...
 // Columns [col_lo, col_hi) of X are updated (ancestor columns in the up-sweep, all RHS columns in the solve).
 // grid = (row chunk, node*2 + h, column tile)
 // ---------------------------------------------------------------------------------------------------------------
@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(UP_THREADS) update_nn_kernel(const NodeDesc* _
                                                                const double* __restrict__ Up, int64_t ldu,
                                                                double* __restrict__ X, int64_t ldx, int col_lo,
                                                                int col_hi, const double* __restrict__ W,
-                                                               int64_t w_stride_half, int w_col_off) {
+                                                               int64_t w_stride_node, int w_col_off) {
   __shared__ double st[UP_TC][UP_QC + 1];  // coefficient slab: UP_QC factor columns x UP_TC target columns
   const NodeDesc nd = nodes[blockIdx.y >> 1];
   const int h = blockIdx.y & 1;
@@ -731,7 +731,8 @@ __global__ void __launch_bounds__(UP_THREADS) update_nn_kernel(const NodeDesc* _
   if (c0 >= col_hi) return;
   const int nc = min(UP_TC, col_hi - c0);
   const int r = nd.r;
-  const double* T = W + ((int64_t)(blockIdx.y >> 1) * 2 + (1 - h)) * w_stride_half;  // T(:, c) for X column c at c + w_col_off
+  const double* T = W + (int64_t)(blockIdx.y >> 1) * w_stride_node + (h ? r : 0);  // T(:, c) for X column c at c + w_col_off
+  const int ldw = 2 * r;
   const int i = row0 + threadIdx.x;
   const bool active = i < nh;
   double acc[UP_TC];
@@ -743,7 +744,7 @@ __global__ void __launch_bounds__(UP_THREADS) update_nn_kernel(const NodeDesc* _
     __syncthreads();
     for (int t = threadIdx.x; t < UP_QC * UP_TC; t += UP_THREADS) {
       const int q = t % UP_QC, c = t / UP_QC;
-      st[c][q] = (q < nq && c < nc) ? T[(int64_t)(c0 + c + w_col_off) * r + q0 + q] : 0.0;
+      st[c][q] = (q < nq && c < nc) ? T[(int64_t)(c0 + c + w_col_off) * ldw + q0 + q] : 0.0;
     }
     __syncthreads();
     if (active) {

@@ -241,6 +241,17 @@ int bgp_hodlr_last_work(const bgp_hodlr_t* h, double* w6);
 int bgp_hodlr_set_profiling(bgp_hodlr_t* h, int on);
 int bgp_hodlr_last_aca_profile(const bgp_hodlr_t* h, double* p5);
 
+/* Diagnostics: the dense building blocks of the big-rank Woodbury step (csrc/hodlr_lu.cuh, csrc/gemm_dmma.cuh),
+ * callable on their own with HOST pointers so the tests can check them against LAPACK.
+ *   bgp_selftest_lu: S (n x n, column-major) is LU-factored with partial pivoting in blocks of 32, R (n x nrhs,
+ *     column-major, ld n) is overwritten by S^-1 R, *logdet = log|det S|      (stands in for Eigen::FullPivLU,
+ *     hodlr.h:228-234, :90-93, :250).
+ *   bgp_selftest_gemm: C (m x n, column-major ldc) -= A' B' (or += with atomics); A' (m,k) = a_kcontig ? A[m*lda+k]
+ *     : A[k*lda+m]; B' (k,n) = B[n*ldb+k] (b_kcontig must be 1). */
+int bgp_selftest_lu(int32_t n, int32_t nrhs, const double* S_host, double* R_host, double* logdet);
+int bgp_selftest_gemm(int32_t a_kcontig, int32_t b_kcontig, int32_t m, int32_t n, int32_t k, const double* A_host,
+                      int64_t lda, const double* B_host, int64_t ldb, double* C_host, int64_t ldc, int32_t atomic_add);
+
 /* Multi-GPU exchange step: after the local sub-tree is factored, the rows this
  * shard owns of the shared top-level factor panel are exported, all-gathered by the host
  * (torch.distributed / NCCL), imported, and the top nodes are finished redundantly.

@@ -1,0 +1,121 @@
+# -*- coding: utf-8 -*-
+"""The dense building blocks of the big-rank Woodbury step (csrc/hodlr_lu.cuh, csrc/gemm_dmma.cuh) against LAPACK,
+and the HODLR solver on cases whose ranks take that path (2r > 142) against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(lib, a_k, A, B, Cm, atomic):
+    """A: stored array (column-major semantics handled by the caller), returns updated C (m x n)."""
+    from george_b200 import _lib
+    m, n = Cm.shape
+    k = A.shape[1] if a_k == 0 else A.shape[0]
+    # column-major storage = Fortran order
+    Af = np.asfortranarray(A)
+    Bf = np.asfortranarray(B)
+    Cf = np.asfortranarray(Cm.copy())
+    _lib.check(lib.bgp_selftest_gemm(a_k, 1, m, n, k, _lib.ptr(Af), Af.shape[0], _lib.ptr(Bf), Bf.shape[0],
+                                     _lib.ptr(Cf), Cf.shape[0], int(atomic)))
+    return Cf
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (128, 128, 16), (200, 150, 70), (1000, 1, 32), (37, 300, 4100),
+                                   (513, 129, 33)])
+@pytest.mark.parametrize("a_k", [0, 1])
+def test_dmma_gemm_variants(gpu, m, n, k, a_k):
+    from george_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(m * 7 + n * 3 + k)
+    Ap = rng.normal(size=(m, k))          # A' (m x k)
+    Bp = rng.normal(size=(k, n))          # B' (k x n), stored K x N column-major  (b_kcontig)
+    C0 = rng.normal(size=(m, n))
+    A_store = Ap if a_k == 0 else Ap.T.copy()   # a_k=0: M x K column-major; a_k=1: K x M column-major
+    for atomic in (0, 1):
+        got = _gemm(lib, a_k, A_store, Bp, C0, atomic)
+        want = C0 + Ap @ Bp if atomic else C0 - Ap @ Bp
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-11 * max(1.0, np.sqrt(k)))
+
+
+@pytest.mark.parametrize("n,nrhs", [(1, 1), (31, 3), (32, 1), (33, 5), (64, 64), (150, 1), (257, 200), (700, 130)])
+def test_blocked_lu_vs_lapack(gpu, n, nrhs):
+    from george_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(n + nrhs)
+    if n >= 2 and n % 2 == 0:
+        r = n // 2  # the Woodbury shape [[I, A], [B, I]]
+        S = np.eye(n)
+        S[:r, r:] = rng.normal(size=(r, r)) / np.sqrt(r)
+        S[r:, :r] = rng.normal(size=(r, r)) / np.sqrt(r)
+    else:
+        S = rng.normal(size=(n, n)) + 0.5 * np.eye(n)
+    R = rng.normal(size=(n, nrhs))
+    Sf = np.asfortranarray(S)
+    Rf = np.asfortranarray(R.copy())
+    ld = C.c_double(0.0)
+    _lib.check(lib.bgp_selftest_lu(n, nrhs, _lib.ptr(Sf), _lib.ptr(Rf), C.byref(ld)))
+    want = np.linalg.solve(S, R)
+    cond = np.linalg.cond(S)
+    assert np.linalg.norm(Rf - want) <= 1e-13 * cond * np.linalg.norm(want) + 1e-14
+    assert abs(ld.value - np.linalg.slogdet(S)[1]) <= 1e-11 * max(1.0, abs(ld.value)) * max(1.0, np.log10(cond))
+
+
+def test_big_rank_levels_match_oracle(gpu, oracle):
+    """ExpSquared + ExpSine2 at N = 16384: the reference algorithm's ranks reach ~75 at the top (2r > 142), so the top
+    levels take the blocked-LU / DMMA path and the lower ones the shared-memory path."""
+    import bench
+    from george_b200.solvers._hodlr import HODLRSolver
+    from george_b200._spec import flatten
+    n = 16384
+    kernel = bench.make_kernel("cfg5")
+    rng = np.random.default_rng(1234)
+    x = np.sort(rng.uniform(0, 10 * n / 1000, n))[:, None]
+    yerr = 0.1 * np.ones(n)
+    y = np.sin(x[:, 0]) + 0.1 * rng.normal(size=n)
+    o = oracle.HODLR(flatten(kernel), x, yerr, min_size=100, tol=1e-10, seed=42, rng_mode=0)
+    s = HODLRSolver()
+    s.compute(kernel, x, yerr, min_size=100, tol=1e-10, seed=42)
+    gn, on = s.nodes(), o.nodes()
+    assert max(nd["rank"] for nd in on) > 71 and max(nd["rank"] for nd in gn) > 71
+    # the tail of this kernel's ACA runs at the rounding-noise floor (accepted pivots ~1e-13), so the last few ranks
+    # depend on the last bits of exp/sin: same tree, ranks within a few of the oracle's, values to tolerance
+    assert [nd["is_leaf"] for nd in gn] == [nd["is_leaf"] for nd in on]
+    assert max(abs(a_["rank"] - b_["rank"]) for a_, b_ in zip(gn, on)) <= 8
+    assert abs(s.log_determinant - o.log_determinant) <= 1e-9 * abs(o.log_determinant)
+    assert abs(s.dot_solve(y) - o.dot_solve(y)) <= 1e-7 * abs(o.dot_solve(y))
+    a, ao = s.apply_inverse(y)[:, 0], o.apply_inverse(y)
+    assert np.linalg.norm(a - ao) <= 1e-6 * np.linalg.norm(ao)
+
+
+@pytest.mark.parametrize("kname", ["expsq", "m52_3d"])
+def test_every_level_through_the_big_path(gpu, oracle, monkeypatch, kname):
+    """BGP_SMALL_RANK_LIMIT=0 sends all levels (any rank) through the DMMA Gram/update + blocked LU path; the result
+    must agree with the shared-memory path and the oracle."""
+    from george_b200 import kernels as K
+    from george_b200.solvers._hodlr import HODLRSolver
+    from george_b200._spec import flatten
+    rng = np.random.default_rng(5)
+    n = 3000
+    if kname == "m52_3d":
+        x = rng.uniform(0, 1, (n, 3))
+        x = x[np.argsort(x[:, 0])]
+        kernel, tol = 1.0 * K.Matern52Kernel(0.5, ndim=3), 1e-12
+    else:
+        x = np.sort(rng.uniform(0, 10 * n / 1000, n))[:, None]
+        kernel, tol = 1.0 * K.ExpSquaredKernel(1.0), 1e-10
+    yerr = 0.1 * np.ones(n)
+    y = rng.normal(size=(n, 3))
+    res = {}
+    for limit in ("142", "0"):
+        monkeypatch.setenv("BGP_SMALL_RANK_LIMIT", limit)
+        s = HODLRSolver()
+        s.compute(kernel, x, yerr, min_size=100, tol=tol, seed=42)
+        res[limit] = (s.log_determinant, s.apply_inverse(y), s.dot_solve(y[:, 0]))
+    o = oracle.HODLR(flatten(kernel), x, yerr, min_size=100, tol=tol, seed=42, rng_mode=0)
+    for limit in res:
+        assert abs(res[limit][0] - o.log_determinant) <= 1e-9 * abs(o.log_determinant)
+        assert abs(res[limit][2] - o.dot_solve(y[:, 0])) <= 1e-7 * abs(o.dot_solve(y[:, 0]))
+    assert np.linalg.norm(res["0"][1] - res["142"][1]) <= 1e-8 * np.linalg.norm(res["142"][1])
