@@ -50,6 +50,18 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ double gd_ld_global(const double* p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];\n" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void gd_st_global(double* p, double v) {
+  asm volatile("st.global.f64 [%0], %1;\n" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void gd_red_add_global(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(p), "d"(v) : "memory");
+}
+
 // load one BK-slab of an operand tile (128 rows/cols x 16 k) into shared memory
 template <bool KCONTIG>
 __device__ __forceinline__ void gd_load_tile(double* sm, const double* __restrict__ G, int64_t ld, int mn0, int mn_max,
@@ -144,22 +156,42 @@ __global__ void __launch_bounds__(GD_THREADS) gemm_dmma_kernel(const GemmDesc* _
   }
   cp_async_wait<0>();
 
-  // epilogue: thread holds C(m = .. + lr, n = .. + 2*lc + {0,1})
+  // epilogue: thread holds C(m = .. + lr, n = .. + 2*lc + {0,1}).  C is read-modify-written with explicit .global
+  // accesses (the descriptor's pointer is generic to the compiler, which would otherwise serialise 64 dependent
+  // LD -> ST round trips per thread): 16 loads in flight per batch, fire-and-forget reductions in the split-K mode.
   const int op = d.mode & 0xff;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = m0 + wm * 64 + i * 8 + lr;
-    if (m >= d.M) continue;
+  for (int i2 = 0; i2 < 8; i2 += 2) {
+    double cv[2][4][2];
+    if (op == GD_SUB) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+      for (int ii = 0; ii < 2; ++ii) {
+        const int m = m0 + wm * 64 + (i2 + ii) * 8 + lr;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int n = n0 + wn * 32 + j * 8 + 2 * lc + e;
-        if (n >= d.N) continue;
-        if (lower && m < n) continue;
-        double* c = d.C + (int64_t)n * d.ldc + m;
-        if (op == GD_SUB) *c -= acc[i][j][e];
-        else atomicAdd(c, acc[i][j][e]);
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int n = n0 + wn * 32 + j * 8 + 2 * lc + e;
+            const bool ok = m < d.M && n < d.N && !(lower && m < n);
+            cv[ii][j][e] = ok ? gd_ld_global(d.C + (int64_t)n * d.ldc + m) : 0.0;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int ii = 0; ii < 2; ++ii) {
+      const int m = m0 + wm * 64 + (i2 + ii) * 8 + lr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int n = n0 + wn * 32 + j * 8 + 2 * lc + e;
+          const bool ok = m < d.M && n < d.N && !(lower && m < n);
+          if (!ok) continue;
+          double* c = d.C + (int64_t)n * d.ldc + m;
+          if (op == GD_SUB) gd_st_global(c, cv[ii][j][e] - acc[i2 + ii][j][e]);
+          else gd_red_add_global(c, acc[i2 + ii][j][e]);
+        }
       }
     }
   }

@@ -22,7 +22,7 @@
 namespace bgp {
 
 constexpr int LU_NB = 32;
-constexpr int LU_PANEL_THREADS = 1024;
+constexpr int LU_PANEL_THREADS = 512;
 constexpr int LU_TRSM_THREADS = 128;
 
 struct LuNode {
@@ -99,10 +99,27 @@ __global__ void __launch_bounds__(LU_PANEL_THREADS) lu_panel_kernel(const LuNode
     const double dkk = srow[j];
     if (threadIdx.x == 0) ld += log(fabs(dkk));
     const double inv = 1.0 / dkk;
+    // scale the column and apply the rank-1 update to the rest of the panel: the row's entries are fetched in batches
+    // of 16 explicit global loads (S comes from a descriptor, so plain accesses would serialise on possible aliasing)
     for (int i = col + 1 + threadIdx.x; i < n; i += blockDim.x) {
-      const double l = cj[i] * inv;
-      cj[i] = l;
-      for (int jj = j + 1; jj < nb; ++jj) S[(int64_t)(k0 + jj) * n + i] -= l * srow[jj];
+      const double l = gd_ld_global(cj + i) * inv;
+      gd_st_global(cj + i, l);
+      double* ri = S + (int64_t)k0 * n + i;  // element (i, k0 + jj) at ri[jj * n]
+#pragma unroll
+      for (int h0 = 0; h0 < LU_NB; h0 += 16) {
+        if (h0 + 15 <= j || h0 >= nb) continue;
+        double rv[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int jj = h0 + q;
+          rv[q] = (jj > j && jj < nb) ? gd_ld_global(ri + (int64_t)jj * n) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int jj = h0 + q;
+          if (jj > j && jj < nb) gd_st_global(ri + (int64_t)jj * n, rv[q] - l * srow[jj]);
+        }
+      }
     }
     __syncthreads();
   }

@@ -19,6 +19,7 @@ for name, kernel, n, ms, exhaust in [
     ("expsq", 1.0 * kernels.ExpSquaredKernel(1.0), 20000, 100, "dense"),
     ("m32", 1.0 * kernels.Matern32Kernel(1.0), 16384, 256, "lowrank"),
     ("odd", 1.0 * kernels.ExpSquaredKernel(1.0), 8191, 100, "dense"),
+    ("m32dense", 1.0 * kernels.Matern32Kernel(1.0), 6000, 100, "dense"),   # big-rank (blocked LU) top levels
 ]:
     rng = np.random.default_rng(1234)
     x = np.sort(rng.uniform(0, 10 * n / 1000, n)); yerr = 0.1 * np.ones(n); y = np.sin(x) + 0.1 * rng.normal(size=n)
