@@ -58,6 +58,11 @@ SIGNATURES = {
     "bgp_kmat_x2_gradient_general": (C.c_int, [_specp, _p, _i64, _p, _i64, _p]),
     "bgp_kmat_symmetric_dev": (C.c_int, [_specp, _p, _i64, _p, _p, _i64]),
     "bgp_kmat_general_dev": (C.c_int, [_specp, _p, _i64, _p, _i64, _p, _i64]),
+    "bgp_kmat_matvec": (C.c_int, [_specp, _p, _i64, _p, _i64, _p, _p, _i64, _p]),
+    "bgp_kmat_matvec_dev": (C.c_int, [_specp, _p, _i64, _p, _i64, _p, _p, _i64, _p]),
+    "bgp_kmat_gradient_contract": (C.c_int, [_specp, _p, _p, _i64, _p, _p]),
+    "bgp_dense_grad_terms": (C.c_int, [_p, _p, _p, _p, _p, _p]),
+    "bgp_hodlr_grad_terms": (C.c_int, [_p, _p, _p, _p, _p, _p]),
     "bgp_dense_create": (C.c_int, [C.POINTER(_p)]),
     "bgp_dense_destroy": (None, [_p]),
     "bgp_dense_compute": (C.c_int, [_p, _specp, _p, _i64, _i32, _p]),

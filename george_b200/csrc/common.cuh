@@ -156,6 +156,25 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
                : "memory");
 }
 
+// cooperative tile load of `count` doubles; TMA bulk when 16-byte aligned & sized, plain loads otherwise.
+// `bar` is a CTA-shared mbarrier already initialised with count 1; `*phase` flips on every TMA use.
+__device__ __forceinline__ void load_coords(double* dst, const double* __restrict__ src, int count, uint64_t* bar,
+                                            uint32_t& phase) {
+  const uint32_t bytes = (uint32_t)count * 8u;
+  const bool bulk = ((bytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && bytes > 0;
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, bytes);
+      tma_load_1d(dst, src, bytes, bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+  } else {
+    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+  }
+}
+
 #endif  // __CUDACC__
 
 }  // namespace bgp

@@ -6,6 +6,7 @@
 // the upper factor U = L^T, basic.py:68) and never leaves HBM.  log-det = 2 sum log L_ii (basic.py:69).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -16,6 +17,10 @@ namespace bgp {
 int upload_program(const DevProgram& P, DevBuf<DevProgram>& buf, cudaStream_t s);
 int kmat_symmetric_launch(const DevProgram* dprog, int nd, const double* x, int64_t n, const double* diag_add,
                           double* out, int64_t ld, cudaStream_t s);
+int kmat_grad_contract_launch(const DevProgram* dprog, int nd, int np, const unsigned* which_dev, const double* x,
+                              int64_t n, const double* M, int64_t ldm, const double* alpha, double ca, double cm,
+                              double* g_dev, double* diag_dev, DevBuf<double>& scratch, cudaStream_t s);
+int fill_identity_launch(double* A, int64_t n, cudaStream_t s);
 
 constexpr int DN_NB = 64;   // inner panel width (diagonal block in shared memory)
 constexpr int DN_OB = 256;  // outer block: trailing updates beyond it run with K = 256 on the tensor pipe
@@ -186,6 +191,114 @@ __global__ void __launch_bounds__(128) trsv_block_kernel(const double* __restric
     if (j < nb) x[j] = w[j];
 }
 
+// ---- few right-hand sides (log_likelihood's single solve, predict's alpha): one launch per 64-column block ---------
+// The generic path above spends ~30 us per block in a one-thread-per-RHS substitution; with 1..8 right-hand sides the
+// solve is a chain of n/64 dependent steps whose useful work is reading L once (8 n^2 / 2 bytes per sweep), so every
+// step is ONE launch: each CTA redundantly solves the 64 x 64 diagonal block with a warp per right-hand side (two
+// entries per lane, pivots broadcast by shuffle) and then applies it to its own 256 rows (forward) or 256 columns
+// (backward) of the panel.  The solved block goes to a second buffer so that no CTA reads entries another one is
+// writing: forward reads B and writes Y, backward reads Y and writes the result back into B.
+constexpr int DS_MAX_RHS = 8;
+constexpr int DS_ROWS = 256;
+
+__device__ __forceinline__ void load_diag_block(double (*l)[DN_NB + 1], const double* __restrict__ Lkk, int64_t ld, int nb) {
+  for (int t = threadIdx.x; t < DN_NB * DN_NB; t += blockDim.x) {
+    const int i = t % DN_NB, j = t / DN_NB;
+    l[i][j] = (i < nb && j < nb) ? Lkk[(int64_t)j * ld + i] : (i == j ? 1.0 : 0.0);
+  }
+}
+
+// step k0 of  L y = b :  Y[k0:k0+nb] = L_kk^-1 B[k0:k0+nb] ;  B[k0+nb:] -= L[k0+nb:, k0:k0+nb] Y[k0:k0+nb]
+template <int NR>
+__global__ void __launch_bounds__(DS_ROWS) trsv_fwd_step_kernel(const double* __restrict__ L, int64_t ld, int64_t n,
+                                                                int64_t k0, int nb, double* __restrict__ B, int64_t ldb,
+                                                                double* __restrict__ Y, int64_t ldy, int nrhs) {
+  __shared__ double l[DN_NB][DN_NB + 1];
+  __shared__ double xs[DS_MAX_RHS][DN_NB];
+  load_diag_block(l, L + k0 * ld + k0, ld, nb);
+  for (int t = threadIdx.x; t < DS_MAX_RHS * DN_NB; t += blockDim.x) xs[t / DN_NB][t % DN_NB] = 0.0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (w < nrhs) {
+    const double* b = B + (int64_t)w * ldb + k0;
+    double w0 = (lane < nb) ? b[lane] : 0.0, w1 = (lane + 32 < nb) ? b[lane + 32] : 0.0;
+    for (int j = 0; j < nb; ++j) {
+      const double xj = __shfl_sync(0xffffffffu, (j < 32) ? w0 : w1, j & 31) / l[j][j];
+      if (j < 32) {
+        if (lane == j) w0 = xj; else if (lane > j) w0 -= l[lane][j] * xj;
+        w1 -= l[lane + 32][j] * xj;
+      } else {
+        const int jj = j - 32;
+        if (lane == jj) w1 = xj; else if (lane > jj) w1 -= l[lane + 32][j] * xj;
+      }
+    }
+    xs[w][lane] = w0; xs[w][lane + 32] = w1;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0)
+    for (int t = threadIdx.x; t < nrhs * nb; t += blockDim.x) Y[(int64_t)(t / nb) * ldy + k0 + t % nb] = xs[t / nb][t % nb];
+  const int64_t row = k0 + nb + (int64_t)blockIdx.x * DS_ROWS + threadIdx.x;
+  if (row >= n) return;
+  double acc[NR];
+#pragma unroll
+  for (int c = 0; c < NR; ++c) acc[c] = 0.0;
+  const double* a = L + k0 * ld + row;
+#pragma unroll 8
+  for (int q = 0; q < nb; ++q) {
+    const double v = a[(int64_t)q * ld];
+#pragma unroll
+    for (int c = 0; c < NR; ++c) acc[c] = fma(v, xs[c][q], acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < NR; ++c)
+    if (c < nrhs) B[(int64_t)c * ldb + row] -= acc[c];
+}
+
+// step k0 of  L^T x = y :  X[k0:k0+nb] = L_kk^-T Y[k0:k0+nb] ;  Y[0:k0] -= L[k0:k0+nb, 0:k0]^T X[k0:k0+nb]
+template <int NR>
+__global__ void __launch_bounds__(DS_ROWS) trsv_bwd_step_kernel(const double* __restrict__ L, int64_t ld, int64_t k0,
+                                                                int nb, double* __restrict__ Y, int64_t ldy,
+                                                                double* __restrict__ X, int64_t ldx, int nrhs) {
+  __shared__ double l[DN_NB][DN_NB + 1];
+  __shared__ double xs[DS_MAX_RHS][DN_NB];
+  load_diag_block(l, L + k0 * ld + k0, ld, nb);
+  for (int t = threadIdx.x; t < DS_MAX_RHS * DN_NB; t += blockDim.x) xs[t / DN_NB][t % DN_NB] = 0.0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (w < nrhs) {
+    const double* y = Y + (int64_t)w * ldy + k0;
+    double w0 = (lane < nb) ? y[lane] : 0.0, w1 = (lane + 32 < nb) ? y[lane + 32] : 0.0;
+    for (int j = nb - 1; j >= 0; --j) {
+      const double xj = __shfl_sync(0xffffffffu, (j < 32) ? w0 : w1, j & 31) / l[j][j];
+      if (j >= 32) {
+        const int jj = j - 32;
+        if (lane == jj) w1 = xj; else if (lane < jj) w1 -= l[j][lane + 32] * xj;
+        w0 -= l[j][lane] * xj;
+      } else {
+        if (lane == j) w0 = xj; else if (lane < j) w0 -= l[j][lane] * xj;
+      }
+    }
+    xs[w][lane] = w0; xs[w][lane + 32] = w1;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0)
+    for (int t = threadIdx.x; t < nrhs * nb; t += blockDim.x) X[(int64_t)(t / nb) * ldx + k0 + t % nb] = xs[t / nb][t % nb];
+  // a warp per column c < k0: the 64 entries L[k0:k0+nb, c] are contiguous (512 B)
+  const int64_t c_begin = (int64_t)blockIdx.x * DS_ROWS;
+  const int64_t c_end = min(k0, c_begin + DS_ROWS);
+  for (int64_t c = c_begin + w; c < c_end; c += DS_ROWS / 32) {
+    const double* a = L + c * ld + k0;
+    const double a0 = (lane < nb) ? a[lane] : 0.0, a1 = (lane + 32 < nb) ? a[lane + 32] : 0.0;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      if (r < nrhs) {
+        const double s = warp_sum(fma(a0, xs[r][lane], a1 * xs[r][lane + 32]));
+        if (lane == 0) Y[(int64_t)r * ldy + c] -= s;
+      }
+    }
+  }
+}
+
 __global__ void logdet_diag_kernel(const double* __restrict__ A, int64_t lda, int64_t n, double* out) {
   __shared__ double red[32];
   double s = 0.0;
@@ -228,10 +341,28 @@ struct bgp_dense {
   double log_det = 0.0;
   DevBuf<DevProgram> d_prog;
   DevBuf<double> d_x, d_yerr, d_diag, d_A, d_rhs, d_scalar;
+  DevBuf<double> d_tmp;              // second buffer of the few-RHS solve
+  DevBuf<double> d_inv, d_gscratch;  // grad_terms: K^-1 (n x n) and the contraction partials
+  DevBuf<unsigned> d_which;
+  bool has_inputs = false;           // d_x / d_prog describe the factor in d_A (false after import_factor)
+  int ndim = 0, n_params = 0;
   DevBuf<int> d_info;
   DevBuf<GemmDesc> d_gdesc;
   double t_ms[2] = {0, 0};
 };
+
+// outer block width (a multiple of DN_NB); BGP_DENSE_OB overrides the default for tuning runs
+static int64_t dense_outer_block() {
+  static int64_t ob = 0;
+  if (ob == 0) {
+    ob = DN_OB;
+    if (const char* e = getenv("BGP_DENSE_OB")) {
+      const long v = atol(e);
+      if (v >= DN_NB && v <= 4096 && v % DN_NB == 0) ob = v;
+    }
+  }
+  return ob;
+}
 
 static int dense_potrf(bgp_dense* h) {
   const int64_t n = h->n;
@@ -241,8 +372,9 @@ static int dense_potrf(bgp_dense* h) {
   std::vector<GemmDesc> descs;
   struct Step { int64_t k0; int nb; int64_t rem; int inner_desc, outer_desc; };
   std::vector<Step> steps;
-  for (int64_t J0 = 0; J0 < n; J0 += DN_OB) {
-    const int ob = (int)std::min<int64_t>(DN_OB, n - J0);
+  const int64_t OB = dense_outer_block();
+  for (int64_t J0 = 0; J0 < n; J0 += OB) {
+    const int ob = (int)std::min<int64_t>(OB, n - J0);
     for (int64_t j0 = J0; j0 < J0 + ob; j0 += DN_NB) {
       Step st;
       st.k0 = j0; st.nb = (int)std::min<int64_t>(DN_NB, J0 + ob - j0); st.rem = n - j0 - st.nb;
@@ -291,7 +423,34 @@ static int dense_potrf(bgp_dense* h) {
 }
 
 // X (n x nrhs, column-major ldx) <- K^-1 X on the device
+static int dense_potrs_small(bgp_dense* h, double* X, int nrhs, int64_t ldx) {
+  const int64_t n = h->n;
+  const double* L = h->d_A.p;
+  cudaStream_t s = h->s;
+  BGP_TRY(h->d_tmp.reserve((size_t)n * DS_MAX_RHS, s));
+  double* Y = h->d_tmp.p;
+  for (int64_t k0 = 0; k0 < n; k0 += DN_NB) {
+    const int nb = (int)std::min<int64_t>(DN_NB, n - k0);
+    const int64_t rem = n - k0 - nb;
+    const unsigned g = (unsigned)std::max<int64_t>(1, (rem + DS_ROWS - 1) / DS_ROWS);
+    if (nrhs == 1) trsv_fwd_step_kernel<1><<<g, DS_ROWS, 0, s>>>(L, n, n, k0, nb, X, ldx, Y, n, nrhs);
+    else if (nrhs <= 4) trsv_fwd_step_kernel<4><<<g, DS_ROWS, 0, s>>>(L, n, n, k0, nb, X, ldx, Y, n, nrhs);
+    else trsv_fwd_step_kernel<DS_MAX_RHS><<<g, DS_ROWS, 0, s>>>(L, n, n, k0, nb, X, ldx, Y, n, nrhs);
+    BGP_LAUNCH_CHECK();
+  }
+  for (int64_t k0 = ((n - 1) / DN_NB) * DN_NB; k0 >= 0; k0 -= DN_NB) {
+    const int nb = (int)std::min<int64_t>(DN_NB, n - k0);
+    const unsigned g = (unsigned)std::max<int64_t>(1, (k0 + DS_ROWS - 1) / DS_ROWS);
+    if (nrhs == 1) trsv_bwd_step_kernel<1><<<g, DS_ROWS, 0, s>>>(L, n, k0, nb, Y, n, X, ldx, nrhs);
+    else if (nrhs <= 4) trsv_bwd_step_kernel<4><<<g, DS_ROWS, 0, s>>>(L, n, k0, nb, Y, n, X, ldx, nrhs);
+    else trsv_bwd_step_kernel<DS_MAX_RHS><<<g, DS_ROWS, 0, s>>>(L, n, k0, nb, Y, n, X, ldx, nrhs);
+    BGP_LAUNCH_CHECK();
+  }
+  return BGP_OK;
+}
+
 static int dense_potrs_dev(bgp_dense* h, double* X, int64_t nrhs, int64_t ldx) {
+  if (nrhs <= DS_MAX_RHS) return dense_potrs_small(h, X, (int)nrhs, ldx);
   const int64_t n = h->n;
   const double* L = h->d_A.p;
   cudaStream_t s = h->s;
@@ -333,6 +492,7 @@ void bgp_dense_destroy(bgp_dense_t* h) {
   if (h->s) cudaStreamSynchronize(h->s);
   h->d_prog.release(); h->d_x.release(); h->d_yerr.release(); h->d_diag.release(); h->d_A.release();
   h->d_rhs.release(); h->d_scalar.release(); h->d_info.release(); h->d_gdesc.release();
+  h->d_tmp.release(); h->d_inv.release(); h->d_gscratch.release(); h->d_which.release();
   if (h->s) {
     cudaStreamSynchronize(h->s);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(h->ev[i]);
@@ -356,6 +516,9 @@ int bgp_dense_compute(bgp_dense_t* h, const bgp_kernel_spec_t* spec, const doubl
   if (n <= 0) { set_error("invalid number of points"); return BGP_ERR_INVALID; }
   cudaStream_t s = h->s;
   h->n = n;
+  h->has_inputs = false;
+  h->ndim = ndim;
+  h->n_params = P.n_params_total;
   BGP_TRY(upload_program(P, h->d_prog, s));
   BGP_TRY(h->d_x.reserve((size_t)n * ndim, s));
   BGP_TRY(h->d_yerr.reserve((size_t)n, s));
@@ -389,6 +552,7 @@ int bgp_dense_compute(bgp_dense_t* h, const bgp_kernel_spec_t* spec, const doubl
   }
   h->log_det = ld;
   h->computed = true;
+  h->has_inputs = true;
   return BGP_OK;
 }
 
@@ -464,6 +628,35 @@ int bgp_dense_get_inverse(bgp_dense_t* h, double* out) {
   return bgp_dense_apply_inverse(h, out, n, n);
 }
 
+int bgp_dense_grad_terms(bgp_dense_t* h, const uint32_t* which, const double* r, double* alpha_out, double* g_out,
+                         double* diag_out) {
+  if (!h || !h->computed) { set_error("the solver has not been computed"); return BGP_ERR_NOT_COMPUTED; }
+  if (!h->has_inputs) { set_error("the factor was imported: the handle holds no kernel/coordinates"); return BGP_ERR_NOT_COMPUTED; }
+  const int64_t n = h->n;
+  const int np = h->n_params;
+  cudaStream_t s = h->s;
+  BGP_TRY(h->d_rhs.reserve((size_t)n * 2 + 64, s));
+  double* alpha = h->d_rhs.p;
+  double* dg = h->d_rhs.p + n;       // np <= 64 entries
+  double* ddiag = h->d_rhs.p + n + 64;
+  BGP_CUDA(cudaMemcpyAsync(alpha, r, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+  BGP_TRY(dense_potrs_dev(h, alpha, 1, n));
+  if (alpha_out) BGP_CUDA(cudaMemcpyAsync(alpha_out, alpha, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  if (np > 64) { set_error("gradient supports at most 64 hyper-parameters"); return BGP_ERR_INVALID; }
+  BGP_TRY(h->d_inv.reserve((size_t)n * n, s));
+  BGP_TRY(fill_identity_launch(h->d_inv.p, n, s));
+  BGP_TRY(dense_potrs_dev(h, h->d_inv.p, n, n));
+  BGP_TRY(h->d_which.reserve(std::max(np, 1), s));
+  if (np) BGP_CUDA(cudaMemcpyAsync(h->d_which.p, which, sizeof(unsigned) * np, cudaMemcpyHostToDevice, s));
+  // kernel term of gp.py:457-466 and diag(alpha alpha^T - K^-1) for the white-noise term of gp.py:452-456
+  BGP_TRY(kmat_grad_contract_launch(h->d_prog.p, h->ndim, np, h->d_which.p, h->d_x.p, n, h->d_inv.p, n, alpha, 1.0, -1.0, dg,
+                                    diag_out ? ddiag : nullptr, h->d_gscratch, s));
+  if (np && g_out) BGP_CUDA(cudaMemcpyAsync(g_out, dg, sizeof(double) * np, cudaMemcpyDeviceToHost, s));
+  if (diag_out) BGP_CUDA(cudaMemcpyAsync(diag_out, ddiag, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  BGP_CUDA(cudaStreamSynchronize(s));
+  return BGP_OK;
+}
+
 int bgp_dense_export_factor(bgp_dense_t* h, double* out) {
   if (!h || !h->computed) { set_error("the solver has not been computed"); return BGP_ERR_NOT_COMPUTED; }
   const int64_t n = h->n;
@@ -483,6 +676,7 @@ int bgp_dense_import_factor(bgp_dense_t* h, const double* factor, int64_t n, dou
     for (int i = 0; i < 4; ++i) BGP_CUDA(cudaEventCreate(&h->ev[i]));
   }
   h->n = n;
+  h->has_inputs = false;
   BGP_TRY(h->d_A.reserve((size_t)n * n, h->s));
   BGP_TRY(h->d_scalar.reserve(2, h->s));
   BGP_CUDA(cudaMemcpyAsync(h->d_A.p, factor, sizeof(double) * n * n, cudaMemcpyHostToDevice, h->s));

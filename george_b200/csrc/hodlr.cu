@@ -22,6 +22,10 @@
 
 namespace bgp {
 int upload_program(const DevProgram& P, DevBuf<DevProgram>& buf, cudaStream_t s);
+int kmat_grad_contract_launch(const DevProgram* dprog, int nd, int np, const unsigned* which_dev, const double* x,
+                              int64_t n, const double* M, int64_t ldm, const double* alpha, double ca, double cm,
+                              double* g_dev, double* diag_dev, DevBuf<double>& scratch, cudaStream_t s);
+int fill_identity_launch(double* A, int64_t n, cudaStream_t s);
 bool comm_ready();
 int comm_rank();
 int comm_world();
@@ -65,6 +69,8 @@ struct bgp_hodlr {
 
   DevBuf<DevProgram> d_prog;
   DevBuf<double> d_x, d_yerr, d_diag, d_L, d_leaf_logdet, d_node_logdet, d_V, d_U, d_S, d_W, d_scalar, d_rhs;
+  DevBuf<double> d_inv, d_gscratch;          // grad_terms: K^-1 (n x n) and the contraction partials
+  DevBuf<unsigned> d_which;
   LuWorkspace lu_ws;                         // big-rank Woodbury step (hodlr_lu.cuh)
   DevBuf<GemmDesc> d_gram_desc, d_upd_desc;
   std::vector<NodeDesc> h_nodes;             // host copy of d_nodes
@@ -738,6 +744,7 @@ void bgp_hodlr_destroy(bgp_hodlr_t* h) {
   h->d_ticket.release(); h->d_chain_done.release(); h->d_ncols_by_depth.release(); h->d_chain_state.release();
   h->d_a2nodes.release(); h->d_a2states.release(); h->d_epart.release(); h->d_cand.release(); h->d_cand_k.release();
   h->d_cand_words.release(); h->d_cchunk_node.release(); h->d_rchunk_node.release(); h->d_nactive.release();
+  h->d_inv.release(); h->d_gscratch.release(); h->d_which.release();
   h->d_vpart.release(); h->d_upart.release(); h->d_cmax.release(); h->d_stats.release(); h->d_work.release(); h->d_work_count.release();
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   if (h->sA) {
@@ -833,6 +840,37 @@ int bgp_hodlr_get_inverse(bgp_hodlr_t* h, double* out) {
     c[j] = 1.0;
   }
   return bgp_hodlr_apply_inverse(h, out, n, n);  // symmetric: row-/column-major agree
+}
+
+// alpha = K^-1 r, g_p = sum_ij (alpha alpha^T - K^-1)_ij dK_ij/dtheta_p, diag(alpha alpha^T - K^-1): everything
+// GP.grad_log_likelihood (gp.py:406-468) needs from the solver, with K^-1 (solve against the identity, _hodlr.cpp:193-199)
+// and the gradient contraction staying on the device.
+int bgp_hodlr_grad_terms(bgp_hodlr_t* h, const uint32_t* which, const double* r, double* alpha_out, double* g_out,
+                         double* diag_out) {
+  if (!h || !h->computed) { set_error("the solver has not been computed"); return BGP_ERR_NOT_COMPUTED; }
+  if (h->opts.shard_count > 1) { set_error("grad_terms is not available on a sharded factorisation"); return BGP_ERR_INVALID; }
+  const int64_t n = h->n;
+  const int np = h->prog.n_params_total;
+  if (np > 64) { set_error("gradient supports at most 64 hyper-parameters"); return BGP_ERR_INVALID; }
+  cudaStream_t s = h->sA;
+  BGP_TRY(h->d_rhs.reserve((size_t)n * 2 + 64, s));
+  double* alpha = h->d_rhs.p;
+  double* dg = h->d_rhs.p + n;
+  double* ddiag = h->d_rhs.p + n + 64;
+  BGP_CUDA(cudaMemcpyAsync(alpha, r, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+  BGP_TRY(hodlr_solve_dev(h, alpha, 1, n, s, 0));
+  if (alpha_out) BGP_CUDA(cudaMemcpyAsync(alpha_out, alpha, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  BGP_TRY(h->d_inv.reserve((size_t)n * n, s));
+  BGP_TRY(fill_identity_launch(h->d_inv.p, n, s));
+  BGP_TRY(hodlr_solve_dev(h, h->d_inv.p, n, n, s, 0));
+  BGP_TRY(h->d_which.reserve(std::max(np, 1), s));
+  if (np) BGP_CUDA(cudaMemcpyAsync(h->d_which.p, which, sizeof(unsigned) * np, cudaMemcpyHostToDevice, s));
+  BGP_TRY(kmat_grad_contract_launch(h->d_prog.p, h->ndim, np, h->d_which.p, h->d_x.p, n, h->d_inv.p, n, alpha, 1.0, -1.0, dg,
+                                    diag_out ? ddiag : nullptr, h->d_gscratch, s));
+  if (np && g_out) BGP_CUDA(cudaMemcpyAsync(g_out, dg, sizeof(double) * np, cudaMemcpyDeviceToHost, s));
+  if (diag_out) BGP_CUDA(cudaMemcpyAsync(diag_out, ddiag, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  BGP_CUDA(cudaStreamSynchronize(s));
+  return BGP_OK;
 }
 
 int bgp_hodlr_num_nodes(const bgp_hodlr_t* h, int64_t* out) {

@@ -229,20 +229,31 @@ class GP(ModelSet):
         nothing = np.zeros(len(self), dtype=np.float64)
         if not self.recompute(quiet=quiet):
             return nothing
+        n_wn, n_k, n_mean = len(self.white_noise), len(self.kernel), len(self.mean)
+        fused = getattr(self.solver, "grad_terms", None) if (n_wn or n_k) else None
         try:
-            alpha = self._compute_alpha(y, False)
+            if fused is not None:
+                # alpha, the kernel-gradient contraction and diag(alpha alpha^T - K^-1) in one device pass: neither
+                # K^-1 nor the (N, N, P) gradient tensor visits the host (reference gp.py:437-466 forms both)
+                mask = self.kernel.unfrozen_mask
+                terms = fused(self._residual(y), mask.astype(np.uint32))
+                if terms is None:
+                    fused = None
+                else:
+                    alpha, gk, diagA = terms
+            if fused is None:
+                alpha = self._compute_alpha(y, False)
         except ValueError:
             if quiet:
                 return nothing
             raise
 
-        n_wn, n_k = len(self.white_noise), len(self.kernel)
-        if n_wn or n_k:
+        if fused is None and (n_wn or n_k):
             A = np.outer(alpha, alpha) - self.solver.get_inverse()
+            diagA = np.diag(A)
 
         grad = np.empty(len(self))
         pos = 0
-        n_mean = len(self.mean)
         if n_mean:
             try:
                 dmu = self._call_mean_gradient(self._x)
@@ -255,11 +266,16 @@ class GP(ModelSet):
         if n_wn:
             wn = self._call_white_noise(self._x)
             dwn = self._call_white_noise_gradient(self._x)
-            grad[pos:pos + n_wn] = 0.5 * np.sum((np.exp(wn) * np.diag(A))[None, :] * dwn, axis=1)
+            grad[pos:pos + n_wn] = 0.5 * np.sum((np.exp(wn) * diagA)[None, :] * dwn, axis=1)
             pos += n_wn
         if n_k:
-            dK = self.kernel.get_gradient(self._x)
-            grad[pos:pos + n_k] = 0.5 * np.einsum("ijk,ij", dK, A)
+            if fused is not None:
+                grad[pos:pos + n_k] = 0.5 * gk[mask]
+            else:
+                # plug-in solvers without grad_terms: K^-1 comes from the solver, the contraction still runs on the
+                # device without the (N, N, P) tensor
+                mask = self.kernel.unfrozen_mask
+                grad[pos:pos + n_k] = 0.5 * self.kernel.kernel.gradient_contract(mask.astype(np.uint32), self._x, A)[mask]
         return grad
 
     def grad_lnlikelihood(self, y, quiet=False):
@@ -286,10 +302,13 @@ class GP(ModelSet):
         if kernel is None:
             kernel = self.kernel
 
+        if not (return_var or return_cov):
+            # mean only: K(x*, x) alpha evaluated matrix-free on the device (csrc/kmat_ops.cu); the reference forms the
+            # (n*, N) matrix on the host (gp.py:524-528), which stops being possible long before N = 2^18
+            return kernel.matvec(xs, self._x, alpha) + self._call_mean(xs)
+
         Kxs = kernel.get_value(xs, self._x)
         mu = np.dot(Kxs, alpha) + self._call_mean(xs)
-        if not (return_var or return_cov):
-            return mu
 
         KinvKxs = self.solver.apply_inverse(Kxs.T)
         if return_var:

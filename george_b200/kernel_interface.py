@@ -101,6 +101,40 @@ class KernelInterface(object):
                                                    _lib.ptr(out)))
         return out
 
+    # ---- matrix-free consumers (not in the reference: it forms the matrix and calls numpy) --------------------------
+    def matvec(self, x1, x2, v, diag=None):
+        """``K(x1, x2) @ v`` (plus ``diag * v`` for a square operator) without forming the ``(n1, n2)`` matrix:
+        what ``GP.predict`` needs for its mean (reference gp.py:524-528).  ``v``: ``(n2,)`` or ``(n2, k)``."""
+        x1, x2 = _as2d(x1, self.ndim), _as2d(x2, self.ndim)
+        v = np.asarray(v, dtype=np.float64)
+        if v.shape[0] != x2.shape[0] or v.ndim not in (1, 2):
+            raise DimensionMismatch("dimension mismatch")
+        vf = np.asfortranarray(v.reshape(x2.shape[0], -1))
+        out = np.empty((x1.shape[0], vf.shape[1]), dtype=np.float64, order="F")
+        d = None
+        if diag is not None:
+            d = np.ascontiguousarray(diag, dtype=np.float64)
+            if d.shape != (x1.shape[0],) or x1.shape[0] != x2.shape[0]:
+                raise DimensionMismatch("dimension mismatch")
+        same = x1.shape == x2.shape and x1.ctypes.data == x2.ctypes.data  # both C-contiguous here
+        _lib.check(_lib.load().bgp_kmat_matvec(C.byref(self._spec), _lib.ptr(x1), x1.shape[0],
+                                               _lib.ptr(x1 if same else x2), x2.shape[0],
+                                               _lib.ptr(d) if d is not None else None, _lib.ptr(vf), vf.shape[1],
+                                               _lib.ptr(out)))
+        return out[:, 0].copy() if v.ndim == 1 else out
+
+    def gradient_contract(self, which, x, A):
+        """``einsum("ijk,ij", gradient_symmetric(which, x), A)`` without the ``(n, n, P)`` tensor (gp.py:465-466)."""
+        which = self._which(which)
+        x = _as2d(x, self.ndim)
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        if A.shape != (x.shape[0], x.shape[0]):
+            raise DimensionMismatch("dimension mismatch")
+        out = np.zeros(self._size, dtype=np.float64)
+        _lib.check(_lib.load().bgp_kmat_gradient_contract(C.byref(self._spec), _lib.ptr(which), _lib.ptr(x), x.shape[0],
+                                                          _lib.ptr(A), _lib.ptr(out)))
+        return out
+
     def _x_gradient(self, fn, x1, x2):
         x1, x2 = _as2d(x1, self.ndim), _as2d(x2, self.ndim)
         out = np.empty((x1.shape[0], x2.shape[0], self.ndim), dtype=np.float64)

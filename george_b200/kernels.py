@@ -110,6 +110,11 @@ class Kernel(ModelSet):
             return self.kernel.value_diagonal(x1, x2)
         return self.kernel.value_general(x1, x2)
 
+    def matvec(self, x1, x2, v, diag=None):
+        """``get_value(x1, x2) @ v`` evaluated matrix-free on the device (``KernelInterface.matvec``)."""
+        return self.kernel.matvec(np.ascontiguousarray(x1, dtype=np.float64),
+                                  np.ascontiguousarray(x2, dtype=np.float64), v, diag=diag)
+
     def get_gradient(self, x1, x2=None, include_frozen=False):
         mask = np.ones(self.full_size, dtype=bool) if include_frozen else self.unfrozen_mask
         which = mask.astype(np.uint32)

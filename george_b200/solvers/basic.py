@@ -75,6 +75,7 @@ class BasicSolver(object):
         ld = C.c_double()
         _lib.check(lib.bgp_dense_log_determinant(self._handle.ptr, C.byref(ld)))
         self._n = n
+        self._has_inputs = True
         self.log_determinant = ld.value
         self.computed = True
 
@@ -125,6 +126,29 @@ class BasicSolver(object):
         _lib.check(self._handle.lib.bgp_dense_get_inverse(self._handle.ptr, _lib.ptr(out)))
         return out
 
+    def grad_terms(self, r, which):
+        """``(alpha, g, diagA)`` for ``GP.grad_log_likelihood`` (gp.py:406-468), all computed on the device from the
+        stored factor: ``alpha = K^-1 r``, ``g[p] = sum_ij (alpha alpha^T - K^-1)_ij dK_ij/dtheta_p`` over ALL kernel
+        parameters (zeros where ``which`` is 0) and ``diagA = diag(alpha alpha^T - K^-1)``.  Replaces
+        ``get_inverse()`` + ``kernel.get_gradient`` + ``einsum`` on the host.  Returns ``None`` for a solver restored from
+        a pickle (its device handle holds the factor but neither kernel nor coordinates): the caller then composes the
+        same quantities from ``get_inverse`` and ``KernelInterface.gradient_contract``."""
+        self._require()
+        if not getattr(self, "_has_inputs", True):
+            return None
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        if r.shape != (self._n,):
+            raise ValueError("dimension mismatch")
+        which = np.ascontiguousarray(which, dtype=np.uint32)
+        alpha = np.empty(self._n, dtype=np.float64)
+        g = np.zeros(max(which.size, 1), dtype=np.float64)
+        diag = np.empty(self._n, dtype=np.float64)
+        _lib.check(self._grad_terms_call(_lib.ptr(which), _lib.ptr(r), _lib.ptr(alpha), _lib.ptr(g), _lib.ptr(diag)))
+        return alpha, g[:which.size], diag
+
+    def _grad_terms_call(self, which, r, alpha, g, diag):
+        return self._handle.lib.bgp_dense_grad_terms(self._handle.ptr, which, r, alpha, g, diag)
+
     # Device handles cannot be pickled.  Like the reference (which pickles its numpy factor, tests/test_pickle.py:21-36:
     # "Unpickled GP shouldn't need to be computed") the Cholesky factor travels with the pickle and is re-uploaded.
     def __getstate__(self):
@@ -143,6 +167,7 @@ class BasicSolver(object):
         self.__dict__.update(state)
         self._handle = None
         if factor is not None:
+            self._has_inputs = False
             try:
                 self._handle = _DenseHandle()
                 _lib.check(self._handle.lib.bgp_dense_import_factor(self._handle.ptr, _lib.ptr(factor), self._n,

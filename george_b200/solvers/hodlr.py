@@ -44,6 +44,14 @@ class HODLRSolver(BasicSolver):
     def get_inverse(self):
         return self.solver.get_inverse()
 
+    def _require(self):
+        if getattr(self, "solver", None) is None or not self._computed:
+            raise RuntimeError("you must call 'compute' first")
+        self._n = self.solver._n
+
+    def _grad_terms_call(self, which, r, alpha, g, diag):
+        return self.solver._lib.bgp_hodlr_grad_terms(self.solver._ptr, which, r, alpha, g, diag)
+
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_computed"] = False

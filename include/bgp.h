@@ -138,6 +138,25 @@ int bgp_kmat_general_dev(const bgp_kernel_spec_t* spec, const double* x1_dev, in
                          int64_t n2, double* out_dev, int64_t ld);
 
 /* ------------------------------------------------------------------------------------------
+ * Matrix-free consumers of the covariance function (csrc/kmat_ops.cu): the kernel matrix is never formed.
+ *
+ * bgp_kmat_matvec: out (n1 x nrhs, column-major, ld n1) = K(x1, x2) v (n2 x nrhs, column-major, ld n2) [+ diag .* v].
+ *   Replaces `np.dot(kernel.get_value(xs, x), alpha)` of GP.predict (src/george/gp.py:524-528, i.e.
+ *   KernelInterface::value_general kernel_interface.cpp:47-60 followed by a host GEMV) without the (n1, n2) matrix;
+ *   with x1 == x2 and diag = yerr^2 it applies the GP covariance itself (K (K^-1 y) == y round-trip checks at sizes
+ *   where K cannot be stored).  `diag` may be NULL; it requires n1 == n2.
+ * bgp_kmat_gradient_contract: out[p] = sum_ij A_ij dK_ij/dtheta_p for the symmetric gradient
+ *   (kernel_interface.cpp:109-125) and a host matrix A (n, n) row-major: the `einsum("ijk,ij", dK, A)` of
+ *   GP.grad_log_likelihood (gp.py:465-466) without the (n, n, P) tensor.  Unselected parameters (which[p] == 0) give 0.
+ * ------------------------------------------------------------------------------------------ */
+int bgp_kmat_matvec(const bgp_kernel_spec_t* spec, const double* x1, int64_t n1, const double* x2, int64_t n2,
+                    const double* diag, const double* v, int64_t nrhs, double* out);
+int bgp_kmat_matvec_dev(const bgp_kernel_spec_t* spec, const double* x1_dev, int64_t n1, const double* x2_dev,
+                        int64_t n2, const double* diag_dev, const double* v_dev, int64_t nrhs, double* out_dev);
+int bgp_kmat_gradient_contract(const bgp_kernel_spec_t* spec, const uint32_t* which, const double* x, int64_t n,
+                               const double* A, double* out /* n_params */);
+
+/* ------------------------------------------------------------------------------------------
  * Dense solver.  Replaces BasicSolver (src/george/solvers/basic.py:51-121): kernel matrix +
  * yerr^2 on the diagonal, Cholesky, log-det = 2 sum log diag, cho_solve, r @ U, dense inverse.
  * ------------------------------------------------------------------------------------------ */
@@ -161,6 +180,14 @@ int bgp_dense_get_inverse(bgp_dense_t* h, double* out);
  * factor out (n*n, column-major, strictly-upper part zeroed) and load it back into a fresh handle. */
 int bgp_dense_export_factor(bgp_dense_t* h, double* out);
 int bgp_dense_import_factor(bgp_dense_t* h, const double* factor, int64_t n, double log_det);
+/* Everything GP.grad_log_likelihood (gp.py:406-468) needs from the solver, computed on the device from the stored
+ * factor, kernel and coordinates: alpha = K^-1 r (n), g[p] = sum_ij (alpha alpha^T - K^-1)_ij dK_ij/dtheta_p (n_params;
+ * the caller multiplies by 0.5 and selects the unfrozen entries) and diag(alpha alpha^T - K^-1) (n, for the white-noise
+ * term gp.py:452-456).  Replaces solver.get_inverse() (basic.py:116-121) + kernel.get_gradient (N x N x P on the host)
+ * + einsum.  Any output pointer may be NULL.  Returns BGP_ERR_NOT_COMPUTED on a handle restored by
+ * bgp_dense_import_factor (it holds no kernel / coordinates). */
+int bgp_dense_grad_terms(bgp_dense_t* h, const uint32_t* which, const double* r, double* alpha_out, double* g_out,
+                         double* diag_out);
 /* timing of the last compute: [0]=kernel-matrix build ms, [1]=potrf ms (device events). */
 int bgp_dense_last_timing(const bgp_dense_t* h, double* ms2);
 
@@ -212,6 +239,11 @@ int bgp_hodlr_dot_solve(bgp_hodlr_t* h, const double* y, double* out);
 int bgp_hodlr_dot_solve_dev(bgp_hodlr_t* h, const double* y_dev, double* out);
 /* _hodlr.cpp:193-199: dense inverse (n, n). */
 int bgp_hodlr_get_inverse(bgp_hodlr_t* h, double* out);
+
+/* The HODLR counterpart of bgp_dense_grad_terms (K^-1 by solving against the identity on the device, as
+ * _hodlr.cpp:193-199 does on the host).  Not available on a sharded factorisation. */
+int bgp_hodlr_grad_terms(bgp_hodlr_t* h, const uint32_t* which, const double* r, double* alpha_out, double* g_out,
+                         double* diag_out);
 
 /* Tree / index structure introspection (bit-exact parity target; hodlr.h:48-61).
  * Nodes are listed in the reference's PRE-ORDER construction order. */
