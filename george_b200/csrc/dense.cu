@@ -17,55 +17,71 @@ namespace bgp {
 int upload_program(const DevProgram& P, DevBuf<DevProgram>& buf, cudaStream_t s);
 int kmat_symmetric_launch(const DevProgram* dprog, int nd, const double* x, int64_t n, const double* diag_add,
                           double* out, int64_t ld, cudaStream_t s);
+int kmat_symmetric_launch_auto(const DevProgram& P, const DevProgram* dprog, const double* x, int64_t n,
+                               const double* diag_add, double* out, int64_t ld, cudaStream_t s);
 int kmat_grad_contract_launch(const DevProgram* dprog, int nd, int np, const unsigned* which_dev, const double* x,
                               int64_t n, const double* M, int64_t ldm, const double* alpha, double ca, double cm,
                               double* g_dev, double* diag_dev, DevBuf<double>& scratch, cudaStream_t s);
 int fill_identity_launch(double* A, int64_t n, cudaStream_t s);
 
 constexpr int DN_NB = 64;   // inner panel width (diagonal block in shared memory)
-constexpr int DN_OB = 256;  // outer block: trailing updates beyond it run with K = 256 on the tensor pipe
+constexpr int DN_OB = 1024; // outer block: trailing updates beyond it run with K = 1024 on the tensor pipe (measured on
+                            // config 4: 256 -> 556 ms, 512 -> 512 ms, 1024 -> 497 ms; the epilogue of a tile is amortised over K)
 
-// ---- diagonal block Cholesky (NB x NB) in shared memory; info != 0 when a pivot is not positive ------------------
-__global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ A, int64_t lda, int nb, int* info, int k0) {
-  __shared__ double s[DN_NB][DN_NB + 1];
-  for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) {
-    const int i = t % nb, j = t / nb;
-    s[i][j] = A[(int64_t)j * lda + i];
-  }
+// ---- diagonal block Cholesky (NB x NB): one thread per ROW, the row lives in registers ------------------------------
+// Right-looking, fully unrolled: at step k every thread scales its entry of column k and applies the rank-1 update to
+// its own row; the only exchanges are the pivot and the scaled column, through (double-buffered) shared memory, two
+// barriers per step.  info != 0 when a pivot is not positive (LAPACK dpotrf's info = k+1; scipy raises LinAlgError).
+__global__ void __launch_bounds__(DN_NB) potf2_kernel(double* __restrict__ A, int64_t lda, int nb, int* info, int k0) {
+  __shared__ double col[2][DN_NB];
+  __shared__ double piv[2];
+  const int i = threadIdx.x;
+  double a[DN_NB];
+#pragma unroll
+  for (int j = 0; j < DN_NB; ++j) a[j] = (i < nb && j < nb) ? A[(int64_t)j * lda + i] : (i == j ? 1.0 : 0.0);
+  if (i == 0) piv[0] = a[0];
   __syncthreads();
-  for (int k = 0; k < nb; ++k) {
-    const double d = s[k][k];
-    if (!(d > 0.0)) {  // also catches NaN; LAPACK's dpotrf info = k+1 (scipy raises LinAlgError)
-      if (threadIdx.x == 0 && atomicCAS(info, 0, k0 + k + 1) == 0) {}
+#pragma unroll
+  for (int k = 0; k < DN_NB; ++k) {
+    const double d = piv[k & 1];
+    if (!(d > 0.0)) {  // also catches NaN; uniform: every thread reads the same pivot
+      if (i == 0) atomicCAS(info, 0, k0 + k + 1);
       return;
     }
-    const double l = sqrt(d);
+    const double lkk = sqrt(d);
+    const double lik = (i == k) ? lkk : a[k] / lkk;
+    a[k] = lik;
+    col[k & 1][i] = lik;
     __syncthreads();
-    if (threadIdx.x == 0) s[k][k] = l;
-    for (int i = k + 1 + threadIdx.x; i < nb; i += blockDim.x) s[i][k] /= l;
-    __syncthreads();
-    const int rem = nb - k - 1;
-    for (int t = threadIdx.x; t < rem * rem; t += blockDim.x) {
-      const int i = k + 1 + t % rem, j = k + 1 + t / rem;
-      if (i >= j) s[i][j] -= s[i][k] * s[j][k];
+#pragma unroll
+    for (int j = k + 1; j < DN_NB; ++j) a[j] = fma(-lik, col[k & 1][j], a[j]);  // entries above the diagonal are scratch
+    if (k + 1 < DN_NB) {
+      if (i == k + 1) piv[(k + 1) & 1] = a[k + 1];
+      __syncthreads();
     }
-    __syncthreads();
   }
-  for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) {
-    const int i = t % nb, j = t / nb;
-    A[(int64_t)j * lda + i] = (i >= j) ? s[i][j] : 0.0;  // explicit zeros above the diagonal of the block
+  if (i < nb) {
+#pragma unroll
+    for (int j = 0; j < DN_NB; ++j)
+      if (j < nb) A[(int64_t)j * lda + i] = (j <= i) ? a[j] : 0.0;  // explicit zeros above the diagonal of the block
   }
 }
 
 // ---- panel solve: rows below the diagonal block, L21 = A21 * L11^-T; one row per thread ---------------------------
-__global__ void __launch_bounds__(128) trsm_panel_kernel(double* __restrict__ A, int64_t lda, int64_t rows, int nb,
+// Column-oriented substitution (x_j = w_j / l_jj, then w_q -= x_j l_qj for q > j): the 2016 updates of a row are
+// independent FMAs instead of 64 dependent dot products; the 64 divisions are multiplications by reciprocals computed
+// once per CTA.
+__global__ void __launch_bounds__(128, 1) trsm_panel_kernel(double* __restrict__ A, int64_t lda, int64_t rows, int nb,
                                                          const int* info) {
   __shared__ double l[DN_NB][DN_NB + 1];
+  __shared__ double rl[DN_NB];
   if (*info != 0) return;
-  for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) {
-    const int i = t % nb, j = t / nb;
-    l[i][j] = A[(int64_t)j * lda + i];
+  for (int t = threadIdx.x; t < DN_NB * DN_NB; t += blockDim.x) {
+    const int i = t % DN_NB, j = t / DN_NB;
+    l[i][j] = (i < nb && j < nb) ? A[(int64_t)j * lda + i] : (i == j ? 1.0 : 0.0);
   }
+  __syncthreads();
+  if (threadIdx.x < DN_NB) rl[threadIdx.x] = 1.0 / l[threadIdx.x][threadIdx.x];
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
@@ -75,12 +91,10 @@ __global__ void __launch_bounds__(128) trsm_panel_kernel(double* __restrict__ A,
   for (int j = 0; j < DN_NB; ++j) w[j] = (j < nb) ? row[(int64_t)j * lda] : 0.0;
 #pragma unroll
   for (int j = 0; j < DN_NB; ++j) {
-    if (j < nb) {
-      double s = w[j];
+    const double xj = w[j] * rl[j];
+    w[j] = xj;
 #pragma unroll
-      for (int q = 0; q < j; ++q) s -= w[q] * l[j][q];
-      w[j] = s / l[j][j];
-    }
+    for (int q = j + 1; q < DN_NB; ++q) w[q] = fma(-xj, l[q][j], w[q]);
   }
 #pragma unroll
   for (int j = 0; j < DN_NB; ++j)
@@ -199,12 +213,44 @@ __global__ void __launch_bounds__(128) trsv_block_kernel(const double* __restric
 // (backward) of the panel.  The solved block goes to a second buffer so that no CTA reads entries another one is
 // writing: forward reads B and writes Y, backward reads Y and writes the result back into B.
 constexpr int DS_MAX_RHS = 8;
-constexpr int DS_ROWS = 256;
+constexpr int DS_ROWS = 256;   // rows of the panel per CTA (forward)
+constexpr int DS_COLS = 64;    // columns of the panel per CTA (backward)
 
-__device__ __forceinline__ void load_diag_block(double (*l)[DN_NB + 1], const double* __restrict__ Lkk, int64_t ld, int nb) {
+// diagonal block (identity-padded to 64 x 64) and the reciprocals of its diagonal
+__device__ __forceinline__ void load_diag_block(double (*l)[DN_NB + 1], double* rl, const double* __restrict__ Lkk,
+                                                int64_t ld, int nb) {
   for (int t = threadIdx.x; t < DN_NB * DN_NB; t += blockDim.x) {
     const int i = t % DN_NB, j = t / DN_NB;
     l[i][j] = (i < nb && j < nb) ? Lkk[(int64_t)j * ld + i] : (i == j ? 1.0 : 0.0);
+  }
+  if (threadIdx.x < DN_NB) rl[threadIdx.x] = (threadIdx.x < nb) ? 1.0 / Lkk[(int64_t)threadIdx.x * ld + threadIdx.x] : 1.0;
+}
+
+// warp-level substitution with the 64 x 64 block in shared memory; entries (lane, lane + 32) of the vector per lane
+__device__ __forceinline__ void warp_trsv_lower(const double (*l)[DN_NB + 1], const double* rl, int nb, int lane,
+                                                double& w0, double& w1) {
+  for (int j = 0; j < nb; ++j) {  // L x = b
+    const double xj = __shfl_sync(0xffffffffu, (j < 32) ? w0 : w1, j & 31) * rl[j];
+    if (j < 32) {
+      if (lane == j) w0 = xj; else if (lane > j) w0 = fma(-l[lane][j], xj, w0);
+      w1 = fma(-l[lane + 32][j], xj, w1);
+    } else {
+      const int jj = j - 32;
+      if (lane == jj) w1 = xj; else if (lane > jj) w1 = fma(-l[lane + 32][j], xj, w1);
+    }
+  }
+}
+__device__ __forceinline__ void warp_trsv_lower_t(const double (*l)[DN_NB + 1], const double* rl, int nb, int lane,
+                                                  double& w0, double& w1) {
+  for (int j = nb - 1; j >= 0; --j) {  // L^T x = y
+    const double xj = __shfl_sync(0xffffffffu, (j < 32) ? w0 : w1, j & 31) * rl[j];
+    if (j >= 32) {
+      const int jj = j - 32;
+      if (lane == jj) w1 = xj; else if (lane < jj) w1 = fma(-l[j][lane + 32], xj, w1);
+      w0 = fma(-l[j][lane], xj, w0);
+    } else {
+      if (lane == j) w0 = xj; else if (lane < j) w0 = fma(-l[j][lane], xj, w0);
+    }
   }
 }
 
@@ -214,36 +260,29 @@ __global__ void __launch_bounds__(DS_ROWS) trsv_fwd_step_kernel(const double* __
                                                                 int64_t k0, int nb, double* __restrict__ B, int64_t ldb,
                                                                 double* __restrict__ Y, int64_t ldy, int nrhs) {
   __shared__ double l[DN_NB][DN_NB + 1];
+  __shared__ double rl[DN_NB];
   __shared__ double xs[DS_MAX_RHS][DN_NB];
-  load_diag_block(l, L + k0 * ld + k0, ld, nb);
+  // this thread's row of the panel: issue the loads first so they overlap the substitution
+  const int64_t row = k0 + nb + (int64_t)blockIdx.x * DS_ROWS + threadIdx.x;
+  load_diag_block(l, rl, L + k0 * ld + k0, ld, nb);
   for (int t = threadIdx.x; t < DS_MAX_RHS * DN_NB; t += blockDim.x) xs[t / DN_NB][t % DN_NB] = 0.0;
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (w < nrhs) {
     const double* b = B + (int64_t)w * ldb + k0;
     double w0 = (lane < nb) ? b[lane] : 0.0, w1 = (lane + 32 < nb) ? b[lane + 32] : 0.0;
-    for (int j = 0; j < nb; ++j) {
-      const double xj = __shfl_sync(0xffffffffu, (j < 32) ? w0 : w1, j & 31) / l[j][j];
-      if (j < 32) {
-        if (lane == j) w0 = xj; else if (lane > j) w0 -= l[lane][j] * xj;
-        w1 -= l[lane + 32][j] * xj;
-      } else {
-        const int jj = j - 32;
-        if (lane == jj) w1 = xj; else if (lane > jj) w1 -= l[lane + 32][j] * xj;
-      }
-    }
+    warp_trsv_lower(l, rl, nb, lane, w0, w1);
     xs[w][lane] = w0; xs[w][lane + 32] = w1;
   }
   __syncthreads();
   if (blockIdx.x == 0)
     for (int t = threadIdx.x; t < nrhs * nb; t += blockDim.x) Y[(int64_t)(t / nb) * ldy + k0 + t % nb] = xs[t / nb][t % nb];
-  const int64_t row = k0 + nb + (int64_t)blockIdx.x * DS_ROWS + threadIdx.x;
   if (row >= n) return;
   double acc[NR];
 #pragma unroll
   for (int c = 0; c < NR; ++c) acc[c] = 0.0;
   const double* a = L + k0 * ld + row;
-#pragma unroll 8
+#pragma unroll 16
   for (int q = 0; q < nb; ++q) {
     const double v = a[(int64_t)q * ld];
 #pragma unroll
@@ -255,46 +294,47 @@ __global__ void __launch_bounds__(DS_ROWS) trsv_fwd_step_kernel(const double* __
 }
 
 // step k0 of  L^T x = y :  X[k0:k0+nb] = L_kk^-T Y[k0:k0+nb] ;  Y[0:k0] -= L[k0:k0+nb, 0:k0]^T X[k0:k0+nb]
+// The CTA's 64 columns of the panel (64 x 64, each column 512 contiguous bytes) are staged through shared memory with
+// all loads in flight at once; then one thread per (column, right-hand side) takes the dot product.
 template <int NR>
-__global__ void __launch_bounds__(DS_ROWS) trsv_bwd_step_kernel(const double* __restrict__ L, int64_t ld, int64_t k0,
-                                                                int nb, double* __restrict__ Y, int64_t ldy,
-                                                                double* __restrict__ X, int64_t ldx, int nrhs) {
-  __shared__ double l[DN_NB][DN_NB + 1];
-  __shared__ double xs[DS_MAX_RHS][DN_NB];
-  load_diag_block(l, L + k0 * ld + k0, ld, nb);
+__global__ void __launch_bounds__(256) trsv_bwd_step_kernel(const double* __restrict__ L, int64_t ld, int64_t k0,
+                                                            int nb, double* __restrict__ Y, int64_t ldy,
+                                                            double* __restrict__ X, int64_t ldx, int nrhs) {
+  extern __shared__ __align__(16) double bwd_smem[];  // 71 KB: above the 48 KB static limit, opted in by the launcher
+  double (*l)[DN_NB + 1] = reinterpret_cast<double (*)[DN_NB + 1]>(bwd_smem);
+  double (*tile)[DN_NB + 1] = reinterpret_cast<double (*)[DN_NB + 1]>(bwd_smem + DN_NB * (DN_NB + 1));  // tile[c][q] = L[k0 + q, c_begin + c]
+  double* rl = bwd_smem + (DN_NB + DS_COLS) * (DN_NB + 1);
+  double (*xs)[DN_NB] = reinterpret_cast<double (*)[DN_NB]>(rl + DN_NB);
+  const int64_t c_begin = (int64_t)blockIdx.x * DS_COLS;
+  const int nc = (int)max((int64_t)0, min((int64_t)DS_COLS, k0 - c_begin));
+  for (int t = threadIdx.x; t < DS_COLS * DN_NB; t += blockDim.x) {
+    const int q = t % DN_NB, c = t / DN_NB;
+    tile[c][q] = (c < nc && q < nb) ? L[(c_begin + c) * ld + k0 + q] : 0.0;
+  }
+  load_diag_block(l, rl, L + k0 * ld + k0, ld, nb);
   for (int t = threadIdx.x; t < DS_MAX_RHS * DN_NB; t += blockDim.x) xs[t / DN_NB][t % DN_NB] = 0.0;
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (w < nrhs) {
     const double* y = Y + (int64_t)w * ldy + k0;
     double w0 = (lane < nb) ? y[lane] : 0.0, w1 = (lane + 32 < nb) ? y[lane + 32] : 0.0;
-    for (int j = nb - 1; j >= 0; --j) {
-      const double xj = __shfl_sync(0xffffffffu, (j < 32) ? w0 : w1, j & 31) / l[j][j];
-      if (j >= 32) {
-        const int jj = j - 32;
-        if (lane == jj) w1 = xj; else if (lane < jj) w1 -= l[j][lane + 32] * xj;
-        w0 -= l[j][lane] * xj;
-      } else {
-        if (lane == j) w0 = xj; else if (lane < j) w0 -= l[j][lane] * xj;
-      }
-    }
+    warp_trsv_lower_t(l, rl, nb, lane, w0, w1);
     xs[w][lane] = w0; xs[w][lane + 32] = w1;
   }
   __syncthreads();
   if (blockIdx.x == 0)
     for (int t = threadIdx.x; t < nrhs * nb; t += blockDim.x) X[(int64_t)(t / nb) * ldx + k0 + t % nb] = xs[t / nb][t % nb];
-  // a warp per column c < k0: the 64 entries L[k0:k0+nb, c] are contiguous (512 B)
-  const int64_t c_begin = (int64_t)blockIdx.x * DS_ROWS;
-  const int64_t c_end = min(k0, c_begin + DS_ROWS);
-  for (int64_t c = c_begin + w; c < c_end; c += DS_ROWS / 32) {
-    const double* a = L + c * ld + k0;
-    const double a0 = (lane < nb) ? a[lane] : 0.0, a1 = (lane + 32 < nb) ? a[lane + 32] : 0.0;
+  // thread (c, r0): column c of this CTA's slab, right-hand sides r0, r0 + 4, ...
+  const int c = threadIdx.x % DS_COLS, r0 = threadIdx.x / DS_COLS;
+  if (c >= nc) return;
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      if (r < nrhs) {
-        const double s = warp_sum(fma(a0, xs[r][lane], a1 * xs[r][lane + 32]));
-        if (lane == 0) Y[(int64_t)r * ldy + c] -= s;
-      }
+  for (int rr = 0; rr < (NR + 3) / 4; ++rr) {
+    const int r = r0 + 4 * rr;
+    if (r < nrhs) {
+      double s = 0.0;
+#pragma unroll 16
+      for (int q = 0; q < DN_NB; ++q) s = fma(tile[c][q], xs[r][q], s);
+      Y[(int64_t)r * ldy + c_begin + c] -= s;
     }
   }
 }
@@ -409,7 +449,7 @@ static int dense_potrf(bgp_dense* h) {
     BGP_CUDA(cudaMemcpyAsync(h->d_gdesc.p, descs.data(), sizeof(GemmDesc) * descs.size(), cudaMemcpyHostToDevice, s));
   for (const Step& st : steps) {
     double* Akk = A + st.k0 * n + st.k0;
-    potf2_kernel<<<1, 256, 0, s>>>(Akk, n, st.nb, h->d_info.p, (int)st.k0);
+    potf2_kernel<<<1, DN_NB, 0, s>>>(Akk, n, st.nb, h->d_info.p, (int)st.k0);
     BGP_LAUNCH_CHECK();
     if (st.rem <= 0) break;
     trsm_panel_kernel<<<(unsigned)((st.rem + 127) / 128), 128, 0, s>>>(Akk, n, st.rem, st.nb, h->d_info.p);
@@ -423,7 +463,16 @@ static int dense_potrf(bgp_dense* h) {
 }
 
 // X (n x nrhs, column-major ldx) <- K^-1 X on the device
+constexpr size_t DS_BWD_SMEM = sizeof(double) * ((DN_NB + DS_COLS) * (DN_NB + 1) + DN_NB + DS_MAX_RHS * DN_NB);
+
 static int dense_potrs_small(bgp_dense* h, double* X, int nrhs, int64_t ldx) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(trsv_bwd_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DS_BWD_SMEM);
+    cudaFuncSetAttribute(trsv_bwd_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DS_BWD_SMEM);
+    cudaFuncSetAttribute(trsv_bwd_step_kernel<DS_MAX_RHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DS_BWD_SMEM);
+    attr = true;
+  }
   const int64_t n = h->n;
   const double* L = h->d_A.p;
   cudaStream_t s = h->s;
@@ -440,10 +489,10 @@ static int dense_potrs_small(bgp_dense* h, double* X, int nrhs, int64_t ldx) {
   }
   for (int64_t k0 = ((n - 1) / DN_NB) * DN_NB; k0 >= 0; k0 -= DN_NB) {
     const int nb = (int)std::min<int64_t>(DN_NB, n - k0);
-    const unsigned g = (unsigned)std::max<int64_t>(1, (k0 + DS_ROWS - 1) / DS_ROWS);
-    if (nrhs == 1) trsv_bwd_step_kernel<1><<<g, DS_ROWS, 0, s>>>(L, n, k0, nb, Y, n, X, ldx, nrhs);
-    else if (nrhs <= 4) trsv_bwd_step_kernel<4><<<g, DS_ROWS, 0, s>>>(L, n, k0, nb, Y, n, X, ldx, nrhs);
-    else trsv_bwd_step_kernel<DS_MAX_RHS><<<g, DS_ROWS, 0, s>>>(L, n, k0, nb, Y, n, X, ldx, nrhs);
+    const unsigned g = (unsigned)std::max<int64_t>(1, (k0 + DS_COLS - 1) / DS_COLS);
+    if (nrhs == 1) trsv_bwd_step_kernel<1><<<g, 256, DS_BWD_SMEM, s>>>(L, n, k0, nb, Y, n, X, ldx, nrhs);
+    else if (nrhs <= 4) trsv_bwd_step_kernel<4><<<g, 256, DS_BWD_SMEM, s>>>(L, n, k0, nb, Y, n, X, ldx, nrhs);
+    else trsv_bwd_step_kernel<DS_MAX_RHS><<<g, 256, DS_BWD_SMEM, s>>>(L, n, k0, nb, Y, n, X, ldx, nrhs);
     BGP_LAUNCH_CHECK();
   }
   return BGP_OK;
@@ -532,7 +581,7 @@ int bgp_dense_compute(bgp_dense_t* h, const bgp_kernel_spec_t* spec, const doubl
   square2_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, s>>>(h->d_yerr.p, h->d_diag.p, n);
   BGP_LAUNCH_CHECK();
   BGP_CUDA(cudaEventRecord(h->ev[0], s));
-  BGP_TRY(kmat_symmetric_launch(h->d_prog.p, ndim, h->d_x.p, n, h->d_diag.p, h->d_A.p, n, s));
+  BGP_TRY(kmat_symmetric_launch_auto(P, h->d_prog.p, h->d_x.p, n, h->d_diag.p, h->d_A.p, n, s));
   BGP_CUDA(cudaEventRecord(h->ev[1], s));
   BGP_TRY(dense_potrf(h));
   logdet_diag_kernel<<<1, 1024, 0, s>>>(h->d_A.p, n, n, h->d_scalar.p);

@@ -9,6 +9,7 @@
 // (st.global.v2.f64).  The symmetric build evaluates only tiles on/above the diagonal and writes the mirrored tile
 // through a shared-memory transpose so both stores stay coalesced.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernel_eval.cuh"
 
@@ -181,6 +182,211 @@ __global__ void __launch_bounds__(128) kmat_x_gradient_kernel(const DevProgram* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Specialised builds for the commonest programs:  c * f(r2)  with f in {ExpSquared, Matern32, Matern52, Exp} and an
+// isotropic or axis-aligned metric over ALL input axes (ndim <= 3, no block mask).  The postfix interpreter costs more
+// instruction issue slots than the covariance itself (ncu on the generic kernel, Matern52 3-D: issue slots 83 % busy,
+// FP64 pipe 18 %, 1.1 TB/s of stores); here the evaluator is a POD functor passed by value, the loops over axes are
+// unrolled and nothing is staged but the coordinates.  Same tile geometry, same i <= j evaluation order on diagonal
+// tiles, same arithmetic (metrics.h:76-85 | 108-117, kernels.h radial profiles) as the generic kernels above.
+// ---------------------------------------------------------------------------------------------------------------
+template <int SHAPE, int ND, bool AXIS>
+struct ProfileND {
+  double c;
+  double m[ND];
+  __device__ __forceinline__ double operator()(const double* x1, const double* x2) const {
+    double r2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) {
+      const double d = x1[i] - x2[i];
+      if (AXIS) r2 += d * d * m[i];
+      else r2 += d * d;
+    }
+    if (!AXIS) r2 = r2 * m[0];
+    double f;
+    if (SHAPE == BGP_SHAPE_EXPSQ) f = exp(-0.5 * r2);
+    else if (SHAPE == BGP_SHAPE_M32) { const double r = sqrt(3.0 * r2); f = (1.0 + r) * exp(-r); }
+    else if (SHAPE == BGP_SHAPE_M52) { const double r = sqrt(5.0 * r2); f = (1 + r + 5.0 * r2 / 3.0) * exp(-r); }
+    else f = exp(-sqrt(r2));
+    return c * f;
+  }
+};
+
+template <class Fn, int ND>
+__global__ void __launch_bounds__(KM_THREADS) kmat_general_fn_kernel(const Fn fn, const double* __restrict__ x1,
+                                                                     int64_t n1, const double* __restrict__ x2,
+                                                                     int64_t n2, double* __restrict__ out, int64_t ld) {
+  __shared__ __align__(16) double sx1[KM_TI * ND];
+  __shared__ __align__(16) double sx2[KM_TJ * ND];
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  uint32_t phase = 0;
+  const int64_t i0 = (int64_t)blockIdx.y * KM_TI, j0 = (int64_t)blockIdx.x * KM_TJ;
+  const int ni = (int)min((int64_t)KM_TI, n1 - i0), nj = (int)min((int64_t)KM_TJ, n2 - j0);
+  load_coords(sx1, x1 + i0 * ND, ni * ND, &bar, phase);
+  load_coords(sx2, x2 + j0 * ND, nj * ND, &bar, phase);
+  __syncthreads();
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int ja = 2 * tx, jb = 2 * tx + 1;
+  const bool vec = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && ((j0 & 1) == 0);
+  if (ja < nj) {
+    double xa[ND], xb[ND];
+#pragma unroll
+    for (int q = 0; q < ND; ++q) { xa[q] = sx2[ja * ND + q]; xb[q] = sx2[(jb < nj ? jb : ja) * ND + q]; }
+    for (int i = ty; i < ni; i += KM_THREADS / 64) {
+      const double* xi = sx1 + i * ND;
+      const double va = fn(xi, xa);
+      const double vb = (jb < nj) ? fn(xi, xb) : 0.0;
+      double* o = out + (i0 + i) * ld + j0 + ja;
+      if (vec && jb < nj) {
+        *reinterpret_cast<double2*>(o) = make_double2(va, vb);
+      } else {
+        o[0] = va;
+        if (jb < nj) o[1] = vb;
+      }
+    }
+  }
+}
+
+template <class Fn, int ND>
+__global__ void __launch_bounds__(KM_THREADS) kmat_symmetric_fn_kernel(const Fn fn, const double* __restrict__ x, int64_t n,
+                                                                       const double* __restrict__ diag_add,
+                                                                       double* __restrict__ out, int64_t ld) {
+  if (blockIdx.x < blockIdx.y) return;  // tiles below the diagonal are produced by the mirror store
+  __shared__ __align__(16) double sxi[KS_T * ND];
+  __shared__ __align__(16) double sxj[KS_T * ND];
+  __shared__ double tile[KS_T * (KS_T + 1)];
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  uint32_t phase = 0;
+  const int64_t i0 = (int64_t)blockIdx.y * KS_T, j0 = (int64_t)blockIdx.x * KS_T;
+  const int ni = (int)min((int64_t)KS_T, n - i0), nj = (int)min((int64_t)KS_T, n - j0);
+  const bool on_diag = (blockIdx.x == blockIdx.y);
+  load_coords(sxi, x + i0 * ND, ni * ND, &bar, phase);
+  load_coords(sxj, x + j0 * ND, nj * ND, &bar, phase);
+  __syncthreads();
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  double xj[ND];
+#pragma unroll
+  for (int q = 0; q < ND; ++q) xj[q] = sxj[(tx < nj ? tx : 0) * ND + q];
+  if (on_diag) {
+    if (tx < nj) {
+      for (int i = ty; i < ni && i <= tx; i += KM_THREADS / 64) {
+        double v = fn(sxi + i * ND, xj);
+        if (i == tx && diag_add) v += diag_add[i0 + i];
+        tile[i * (KS_T + 1) + tx] = v;
+      }
+    }
+    __syncthreads();
+    if (tx < nj) {
+      for (int i = ty; i < ni; i += KM_THREADS / 64)
+        out[(i0 + i) * ld + j0 + tx] = (i <= tx) ? tile[i * (KS_T + 1) + tx] : tile[tx * (KS_T + 1) + i];
+    }
+    return;
+  }
+  if (tx < nj) {
+    for (int i = ty; i < ni; i += KM_THREADS / 64) {
+      const double v = fn(sxi + i * ND, xj);
+      out[(i0 + i) * ld + j0 + tx] = v;
+      tile[i * (KS_T + 1) + tx] = v;
+    }
+  }
+  __syncthreads();
+  if (tx < ni) {
+    for (int c = ty; c < nj; c += KM_THREADS / 64) out[(j0 + c) * ld + i0 + tx] = tile[tx * (KS_T + 1) + c];
+  }
+}
+
+// host: does the digested program have the shape  [Constant *] f(metric over all axes) ?
+struct FastShape {
+  int shape = 0, nd = 0;
+  bool axis = false;
+  double c = 1.0, m[3] = {1.0, 1.0, 1.0};
+};
+static bool detect_fast_shape(const DevProgram& P, FastShape* out) {
+  if (P.ndim < 1 || P.ndim > 3) return false;
+  const DevLeaf* S = nullptr;
+  const DevLeaf* C = nullptr;
+  if (P.n_nodes == 1 && P.n_leaves == 1 && P.code[0] == 0) S = &P.leaf[0];
+  else if (P.n_nodes == 3 && P.n_leaves == 2 && P.code[0] == 0 && P.code[1] == 1 && P.code[2] == -2) {
+    if (P.leaf[0].kernel_type == BGP_K_CONSTANT) { C = &P.leaf[0]; S = &P.leaf[1]; }
+    else if (P.leaf[1].kernel_type == BGP_K_CONSTANT) { C = &P.leaf[1]; S = &P.leaf[0]; }
+    else return false;
+  } else return false;
+  switch (S->kernel_type) {
+    case BGP_K_EXP_SQUARED: out->shape = BGP_SHAPE_EXPSQ; break;
+    case BGP_K_MATERN32: out->shape = BGP_SHAPE_M32; break;
+    case BGP_K_MATERN52: out->shape = BGP_SHAPE_M52; break;
+    case BGP_K_EXP: out->shape = BGP_SHAPE_EXP; break;
+    default: return false;
+  }
+  if (S->blocked || S->naxes != P.ndim) return false;
+  for (int i = 0; i < S->naxes; ++i) if (S->axes[i] != i) return false;
+  if (S->metric_type == BGP_METRIC_ISOTROPIC) { out->axis = false; out->m[0] = S->mvec[0]; }
+  else if (S->metric_type == BGP_METRIC_AXIS_ALIGNED) { out->axis = true; for (int i = 0; i < S->naxes; ++i) out->m[i] = S->mvec[i]; }
+  else return false;
+  out->nd = P.ndim;
+  out->c = 1.0;
+  if (C) {  // the constant kernel is summed over its axes (kernels.h:1720-1732): reproduce the additions
+    if (C->naxes < 1) return false;
+    double v = 0.0;
+    for (int a = 0; a < C->naxes; ++a) v += C->rp[0];
+    out->c = v;
+  }
+  return true;
+}
+
+template <int SHAPE, int ND, bool AXIS>
+static int launch_fast(const FastShape& F, bool symmetric, const double* x1, int64_t n1, const double* x2, int64_t n2,
+                       const double* diag_add, double* out, int64_t ld, cudaStream_t s) {
+  typedef ProfileND<SHAPE, ND, AXIS> Fn;
+  Fn fn;
+  fn.c = F.c;
+  for (int i = 0; i < ND; ++i) fn.m[i] = F.m[i];
+  if (symmetric) {
+    const unsigned nt = (unsigned)((n1 + KS_T - 1) / KS_T);
+    if (nt > 65535) { set_error("kmat_symmetric: n too large for one launch"); return BGP_ERR_INVALID; }
+    kmat_symmetric_fn_kernel<Fn, ND><<<dim3(nt, nt), KM_THREADS, 0, s>>>(fn, x1, n1, diag_add, out, ld);
+  } else {
+    dim3 grid((unsigned)((n2 + KM_TJ - 1) / KM_TJ), (unsigned)((n1 + KM_TI - 1) / KM_TI));
+    if (grid.y > 65535) { set_error("kmat_general: n1 too large for one launch"); return BGP_ERR_INVALID; }
+    kmat_general_fn_kernel<Fn, ND><<<grid, KM_THREADS, 0, s>>>(fn, x1, n1, x2, n2, out, ld);
+  }
+  BGP_LAUNCH_CHECK();
+  return BGP_OK;
+}
+template <int SHAPE, int ND>
+static int launch_fast_axis(const FastShape& F, bool symmetric, const double* x1, int64_t n1, const double* x2, int64_t n2,
+                            const double* diag_add, double* out, int64_t ld, cudaStream_t s) {
+  return F.axis ? launch_fast<SHAPE, ND, true>(F, symmetric, x1, n1, x2, n2, diag_add, out, ld, s)
+                : launch_fast<SHAPE, ND, false>(F, symmetric, x1, n1, x2, n2, diag_add, out, ld, s);
+}
+template <int SHAPE>
+static int launch_fast_nd(const FastShape& F, bool symmetric, const double* x1, int64_t n1, const double* x2, int64_t n2,
+                          const double* diag_add, double* out, int64_t ld, cudaStream_t s) {
+  switch (F.nd) {
+    case 1: return launch_fast_axis<SHAPE, 1>(F, symmetric, x1, n1, x2, n2, diag_add, out, ld, s);
+    case 2: return launch_fast_axis<SHAPE, 2>(F, symmetric, x1, n1, x2, n2, diag_add, out, ld, s);
+    default: return launch_fast_axis<SHAPE, 3>(F, symmetric, x1, n1, x2, n2, diag_add, out, ld, s);
+  }
+}
+// returns -1 when the program has no specialised build (the caller then launches the interpreter kernels)
+static int try_launch_fast(const DevProgram& P, bool symmetric, const double* x1, int64_t n1, const double* x2, int64_t n2,
+                           const double* diag_add, double* out, int64_t ld, cudaStream_t s) {
+  static const bool disabled = getenv("BGP_KMAT_GENERIC") != nullptr;  // tuning / A-B runs
+  FastShape F;
+  if (disabled || !detect_fast_shape(P, &F)) return -1;
+  switch (F.shape) {
+    case BGP_SHAPE_EXPSQ: return launch_fast_nd<BGP_SHAPE_EXPSQ>(F, symmetric, x1, n1, x2, n2, diag_add, out, ld, s);
+    case BGP_SHAPE_M32: return launch_fast_nd<BGP_SHAPE_M32>(F, symmetric, x1, n1, x2, n2, diag_add, out, ld, s);
+    case BGP_SHAPE_M52: return launch_fast_nd<BGP_SHAPE_M52>(F, symmetric, x1, n1, x2, n2, diag_add, out, ld, s);
+    case BGP_SHAPE_EXP: return launch_fast_nd<BGP_SHAPE_EXP>(F, symmetric, x1, n1, x2, n2, diag_add, out, ld, s);
+  }
+  return -1;
+}
+
 static size_t kmat_smem_general(int nd) {
   return ((sizeof(KmatSmem) + 15) & ~size_t(15)) + sizeof(double) * ((size_t)KM_TI * nd + 1 + (size_t)KM_TJ * nd + 1);
 }
@@ -217,6 +423,20 @@ int kmat_symmetric_launch(const DevProgram* dprog, int nd, const double* x, int6
   return BGP_OK;
 }
 
+// host program known: specialised build when the program has one, interpreter otherwise
+int kmat_symmetric_launch_auto(const DevProgram& P, const DevProgram* dprog, const double* x, int64_t n,
+                               const double* diag_add, double* out, int64_t ld, cudaStream_t s) {
+  if (n == 0) return BGP_OK;
+  const int r = try_launch_fast(P, true, x, n, x, n, diag_add, out, ld, s);
+  return r >= 0 ? r : kmat_symmetric_launch(dprog, P.ndim, x, n, diag_add, out, ld, s);
+}
+int kmat_general_launch_auto(const DevProgram& P, const DevProgram* dprog, const double* x1, int64_t n1, const double* x2,
+                             int64_t n2, double* out, int64_t ld, cudaStream_t s) {
+  if (n1 == 0 || n2 == 0) return BGP_OK;
+  const int r = try_launch_fast(P, false, x1, n1, x2, n2, nullptr, out, ld, s);
+  return r >= 0 ? r : kmat_general_launch(dprog, P.ndim, x1, n1, x2, n2, out, ld, s);
+}
+
 // upload a digested program to a fresh device buffer
 int upload_program(const DevProgram& P, DevBuf<DevProgram>& buf, cudaStream_t s) {
   BGP_TRY(buf.reserve(1, s));
@@ -251,8 +471,8 @@ static int kmat_host(const bgp_kernel_spec_t* spec, const double* x1, int64_t n1
   const size_t nout = mode == 2 ? (size_t)n1 : (size_t)n1 * (size_t)(mode == 1 ? n1 : n2);
   BGP_TRY(dout.alloc(nout, s));
   if (nout == 0) return BGP_OK;
-  if (mode == 0) BGP_TRY(kmat_general_launch(dprog.p, nd, dx1.p, n1, px2, n2, dout.p, n2, s));
-  else if (mode == 1) BGP_TRY(kmat_symmetric_launch(dprog.p, nd, dx1.p, n1, nullptr, dout.p, n1, s));
+  if (mode == 0) BGP_TRY(kmat_general_launch_auto(P, dprog.p, dx1.p, n1, px2, n2, dout.p, n2, s));
+  else if (mode == 1) BGP_TRY(kmat_symmetric_launch_auto(P, dprog.p, dx1.p, n1, nullptr, dout.p, n1, s));
   else {
     const int blocks = (int)std::min<int64_t>((n1 + 255) / 256, 4 * num_sms());
     kmat_diagonal_kernel<<<blocks, 256, 0, s>>>(dprog.p, dx1.p, px2, n1, dout.p);
@@ -359,7 +579,7 @@ int bgp_kmat_symmetric_dev(const bgp_kernel_spec_t* spec, const double* x_dev, i
   BGP_TRY(build_dev_program(spec, &P));
   DevBuf<DevProgram> dprog;
   BGP_TRY(upload_program(P, dprog, 0));
-  return kmat_symmetric_launch(dprog.p, P.ndim, x_dev, n, diag_add_dev, out_dev, ld, 0);
+  return kmat_symmetric_launch_auto(P, dprog.p, x_dev, n, diag_add_dev, out_dev, ld, 0);
 }
 int bgp_kmat_general_dev(const bgp_kernel_spec_t* spec, const double* x1_dev, int64_t n1, const double* x2_dev,
                          int64_t n2, double* out_dev, int64_t ld) {
@@ -368,7 +588,7 @@ int bgp_kmat_general_dev(const bgp_kernel_spec_t* spec, const double* x1_dev, in
   BGP_TRY(build_dev_program(spec, &P));
   DevBuf<DevProgram> dprog;
   BGP_TRY(upload_program(P, dprog, 0));
-  return kmat_general_launch(dprog.p, P.ndim, x1_dev, n1, x2_dev, n2, out_dev, ld, 0);
+  return kmat_general_launch_auto(P, dprog.p, x1_dev, n1, x2_dev, n2, out_dev, ld, 0);
 }
 
 }  // extern "C"
