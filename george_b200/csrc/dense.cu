@@ -25,6 +25,7 @@ int kmat_grad_contract_launch(const DevProgram* dprog, int nd, int np, const uns
 int fill_identity_launch(double* A, int64_t n, cudaStream_t s);
 
 constexpr int DN_NB = 64;   // inner panel width (diagonal block in shared memory)
+constexpr int DN_MB = 256;  // middle block of the delayed-update hierarchy (see dense_potrf)
 constexpr int DN_OB = 1024; // outer block: trailing updates beyond it run with K = 1024 on the tensor pipe (measured on
                             // config 4: 256 -> 556 ms, 512 -> 512 ms, 1024 -> 497 ms; the epilogue of a tile is amortised over K)
 
@@ -48,8 +49,10 @@ __global__ void __launch_bounds__(DN_NB) potf2_kernel(double* __restrict__ A, in
       if (i == 0) atomicCAS(info, 0, k0 + k + 1);
       return;
     }
-    const double lkk = sqrt(d);
-    const double lik = (i == k) ? lkk : a[k] / lkk;
+    // 1/sqrt(d) (one MUFU + Newton steps) instead of sqrt followed by a division: this scalar chain is the critical
+    // path of the whole factorisation step; the factor entries differ from sqrt/divide by <= 2 ulp
+    const double rinv = rsqrt(d);
+    const double lik = (i == k) ? d * rinv : a[k] * rinv;
     a[k] = lik;
     col[k & 1][i] = lik;
     __syncthreads();
@@ -262,8 +265,14 @@ __global__ void __launch_bounds__(DS_ROWS) trsv_fwd_step_kernel(const double* __
   __shared__ double l[DN_NB][DN_NB + 1];
   __shared__ double rl[DN_NB];
   __shared__ double xs[DS_MAX_RHS][DN_NB];
-  // this thread's row of the panel: issue the loads first so they overlap the substitution
+  // this thread's row of the panel: the 64 loads are issued first so that they are in flight during the substitution
   const int64_t row = k0 + nb + (int64_t)blockIdx.x * DS_ROWS + threadIdx.x;
+  double v[DN_NB];
+  {
+    const double* a = L + k0 * ld + (row < n ? row : k0);
+#pragma unroll
+    for (int q = 0; q < DN_NB; ++q) v[q] = (q < nb && row < n) ? a[(int64_t)q * ld] : 0.0;
+  }
   load_diag_block(l, rl, L + k0 * ld + k0, ld, nb);
   for (int t = threadIdx.x; t < DS_MAX_RHS * DN_NB; t += blockDim.x) xs[t / DN_NB][t % DN_NB] = 0.0;
   __syncthreads();
@@ -281,12 +290,10 @@ __global__ void __launch_bounds__(DS_ROWS) trsv_fwd_step_kernel(const double* __
   double acc[NR];
 #pragma unroll
   for (int c = 0; c < NR; ++c) acc[c] = 0.0;
-  const double* a = L + k0 * ld + row;
-#pragma unroll 16
-  for (int q = 0; q < nb; ++q) {
-    const double v = a[(int64_t)q * ld];
 #pragma unroll
-    for (int c = 0; c < NR; ++c) acc[c] = fma(v, xs[c][q], acc[c]);
+  for (int q = 0; q < DN_NB; ++q) {
+#pragma unroll
+    for (int c = 0; c < NR; ++c) acc[c] = fma(v[q], xs[c][q], acc[c]);
   }
 #pragma unroll
   for (int c = 0; c < NR; ++c)
@@ -404,45 +411,54 @@ static int64_t dense_outer_block() {
   return ob;
 }
 
+// Blocked right-looking Cholesky with DELAYED trailing updates on three nested block sizes (64 | DN_MB | OB): after the
+// panel ending at column e, the rank-64 update touches only the rest of the current DN_MB block; when e closes a DN_MB
+// block its accumulated rank-DN_MB update touches the rest of the current OB block; when e closes an OB block the
+// rank-OB update touches everything to the right.  Almost all flops therefore run as GEMMs with K = OB, whose
+// read-modify-write epilogue of C is amortised over 16x more tensor work than at K = 64.
+static int64_t dense_mid_block(int64_t OB) {
+  static int64_t mb = 0;
+  if (mb == 0) {
+    mb = DN_MB;
+    if (const char* e = getenv("BGP_DENSE_MB")) {
+      const long v = atol(e);
+      if (v >= DN_NB && v % DN_NB == 0) mb = v;
+    }
+  }
+  return (mb < OB && OB % mb == 0) ? mb : OB;
+}
+
 static int dense_potrf(bgp_dense* h) {
   const int64_t n = h->n;
   double* A = h->d_A.p;
   cudaStream_t s = h->s;
   // all trailing-update descriptors of the factorisation, uploaded once
   std::vector<GemmDesc> descs;
-  struct Step { int64_t k0; int nb; int64_t rem; int inner_desc, outer_desc; };
+  struct Step { int64_t k0; int nb; int64_t rem; int desc[3]; };
   std::vector<Step> steps;
   const int64_t OB = dense_outer_block();
-  for (int64_t J0 = 0; J0 < n; J0 += OB) {
-    const int ob = (int)std::min<int64_t>(OB, n - J0);
-    for (int64_t j0 = J0; j0 < J0 + ob; j0 += DN_NB) {
-      Step st;
-      st.k0 = j0; st.nb = (int)std::min<int64_t>(DN_NB, J0 + ob - j0); st.rem = n - j0 - st.nb;
-      st.inner_desc = -1; st.outer_desc = -1;
-      const int64_t nc = J0 + ob - (j0 + st.nb);
-      if (st.rem > 0 && nc > 0) {
-        GemmDesc d;
-        const double* P = A + j0 * n + j0 + st.nb;  // rows below the diagonal block, nb columns
-        d.A = P; d.lda = n; d.B = P; d.ldb = n;     // B' = P^T restricted to the first nc rows of P
-        d.C = A + (j0 + st.nb) * n + j0 + st.nb; d.ldc = n;
-        d.M = (int)st.rem; d.N = (int)nc; d.K = st.nb; d.mode = GD_SUB | GD_LOWER;
-        st.inner_desc = (int)descs.size();
-        descs.push_back(d);
-      }
-      if (j0 + st.nb >= J0 + ob) {  // last inner step of this outer block: big trailing update
-        const int64_t rem2 = n - J0 - ob;
-        if (rem2 > 0) {
-          GemmDesc d;
-          const double* P = A + J0 * n + J0 + ob;
-          d.A = P; d.lda = n; d.B = P; d.ldb = n;
-          d.C = A + (J0 + ob) * n + J0 + ob; d.ldc = n;
-          d.M = (int)rem2; d.N = (int)rem2; d.K = ob; d.mode = GD_SUB | GD_LOWER;
-          st.outer_desc = (int)descs.size();
-          descs.push_back(d);
-        }
-      }
-      steps.push_back(st);
-    }
+  const int64_t MB = dense_mid_block(OB);
+  // C[e:n, e:cend) -= L[e:n, b:e) L[e:cend, b:e)^T   (lower part only)
+  auto add_update = [&](int64_t b, int64_t e, int64_t cend) -> int {
+    if (e >= n || cend <= e || e <= b) return -1;
+    GemmDesc d;
+    const double* P = A + b * n + e;          // rows e.., columns b..e of the factor
+    d.A = P; d.lda = n; d.B = P; d.ldb = n;   // B' = P^T restricted to the first (cend - e) rows of P
+    d.C = A + e * n + e; d.ldc = n;
+    d.M = (int)(n - e); d.N = (int)(cend - e); d.K = (int)(e - b); d.mode = GD_SUB | GD_LOWER;
+    descs.push_back(d);
+    return (int)descs.size() - 1;
+  };
+  for (int64_t j0 = 0; j0 < n; j0 += DN_NB) {
+    Step st;
+    st.k0 = j0; st.nb = (int)std::min<int64_t>(DN_NB, n - j0); st.rem = n - j0 - st.nb;
+    const int64_t e = j0 + st.nb;
+    const int64_t mb0 = (j0 / MB) * MB, mb1 = std::min(n, mb0 + MB);  // the DN_MB block holding this panel
+    const int64_t ob0 = (j0 / OB) * OB, ob1 = std::min(n, ob0 + OB);  // the OB block holding it
+    st.desc[0] = add_update(j0, e, mb1);
+    st.desc[1] = (e == mb1 && MB < OB) ? add_update(mb0, e, ob1) : -1;
+    st.desc[2] = (e == ob1) ? add_update(ob0, e, n) : -1;
+    steps.push_back(st);
   }
   BGP_TRY(h->d_gdesc.reserve(std::max<size_t>(descs.size(), 1), s));
   if (!descs.empty())
@@ -454,10 +470,9 @@ static int dense_potrf(bgp_dense* h) {
     if (st.rem <= 0) break;
     trsm_panel_kernel<<<(unsigned)((st.rem + 127) / 128), 128, 0, s>>>(Akk, n, st.rem, st.nb, h->d_info.p);
     BGP_LAUNCH_CHECK();
-    if (st.inner_desc >= 0)
-      BGP_TRY((gemm_dmma_launch<false, false>(h->d_gdesc.p + st.inner_desc, 1, descs[st.inner_desc].M, descs[st.inner_desc].N, h->d_info.p, s)));
-    if (st.outer_desc >= 0)
-      BGP_TRY((gemm_dmma_launch<false, false>(h->d_gdesc.p + st.outer_desc, 1, descs[st.outer_desc].M, descs[st.outer_desc].N, h->d_info.p, s)));
+    for (int l = 0; l < 3; ++l)
+      if (st.desc[l] >= 0)
+        BGP_TRY((gemm_dmma_launch<false, false>(h->d_gdesc.p + st.desc[l], 1, descs[st.desc[l]].M, descs[st.desc[l]].N, h->d_info.p, s)));
   }
   return BGP_OK;
 }
