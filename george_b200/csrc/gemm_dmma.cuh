@@ -62,32 +62,70 @@ __device__ __forceinline__ void gd_red_add_global(double* p, double v) {
   asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(p), "d"(v) : "memory");
 }
 
-// load one BK-slab of an operand tile (128 rows/cols x 16 k) into shared memory
+// Loader of one operand's BK-slabs (128 rows/cols x 16 k) into shared memory.  Everything that does not depend on the
+// k-slab — the thread's running global pointer, its shared-memory offset and the row-validity bits of its 8 copies — is
+// computed ONCE per tile; per slab only pointer increments and the k-bound test remain (the straightforward version
+// spent ~275 integer / predicate instructions per slab and warp between the barrier and the first DMMA, with the
+// tensor pipe idle: cuobjdump of the previous build).
 template <bool KCONTIG>
-__device__ __forceinline__ void gd_load_tile(double* sm, const double* __restrict__ G, int64_t ld, int mn0, int mn_max,
-                                             int k0, int k_max) {
-  if (KCONTIG) {
-    // global: element (mn, k) at G[mn*ld + k]; shared: sm[mn*GD_LDK + k]
+struct GdLoader {
+  const double* p;  // running pointer: element (mn0 + mn_t, k of the NEXT slab + k_t) of this thread's first copy
+  int64_t gstep;    // global stride between the thread's consecutive copies i -> i + 1
+  int64_t kstep;    // global stride of one BK-slab
+  int soff;         // shared-memory offset of the first copy
+  int kleft;        // K - (k of the thread's first copy in the next slab): copy i is inside K iff its k offset < kleft
+  unsigned okm;     // bit i: row/col of copy i is inside the matrix
+  static constexpr int NCOPY = (GD_BM * GD_BK) / GD_THREADS;                                             // 8
+  static constexpr int DSTEP = KCONTIG ? (GD_THREADS / GD_BK) * GD_LDK : (GD_THREADS / GD_BM) * GD_LDM;  // smem stride
+  __device__ __forceinline__ void init(const double* G, int64_t ld, int mn0, int mn_max, int K) {
+    okm = 0;
+    if (KCONTIG) {
+      // global element (mn, k) at G[mn*ld + k]; shared sm[mn*GD_LDK + k]; copy i: k = tid % 16, mn = tid / 16 + 16 i
+      const int k = threadIdx.x % GD_BK, mn = threadIdx.x / GD_BK;
+      p = G + (int64_t)(mn0 + mn) * ld + k;
+      gstep = (int64_t)(GD_THREADS / GD_BK) * ld;
+      kstep = GD_BK;
+      soff = mn * GD_LDK + k;
+      kleft = K - k;
 #pragma unroll
-    for (int i = 0; i < (GD_BM * GD_BK) / GD_THREADS; ++i) {
-      const int t = threadIdx.x + i * GD_THREADS;
-      const int k = t % GD_BK, mn = t / GD_BK;
-      const bool ok = (mn0 + mn < mn_max) && (k0 + k < k_max);
-      const double* src = ok ? (G + (int64_t)(mn0 + mn) * ld + k0 + k) : G;
-      cp_async8(sm + mn * GD_LDK + k, src, ok);
+      for (int i = 0; i < NCOPY; ++i)
+        if (mn0 + mn + i * (GD_THREADS / GD_BK) < mn_max) okm |= 1u << i;
+    } else {
+      // global element (mn, k) at G[k*ld + mn]; shared sm[k*GD_LDM + mn]; copy i: mn = tid % 128, k = tid / 128 + 2 i
+      const int mn = threadIdx.x % GD_BM, k = threadIdx.x / GD_BM;
+      p = G + (int64_t)k * ld + mn0 + mn;
+      gstep = (int64_t)(GD_THREADS / GD_BM) * ld;
+      kstep = (int64_t)GD_BK * ld;
+      soff = k * GD_LDM + mn;
+      kleft = K - k;
+      if (mn0 + mn < mn_max) okm = 0xffu;
     }
-  } else {
-    // global: element (mn, k) at G[k*ld + mn]; shared: sm[k*GD_LDM + mn]
-#pragma unroll
-    for (int i = 0; i < (GD_BM * GD_BK) / GD_THREADS; ++i) {
-      const int t = threadIdx.x + i * GD_THREADS;
-      const int mn = t % GD_BM, k = t / GD_BM;
-      const bool ok = (mn0 + mn < mn_max) && (k0 + k < k_max);
-      const double* src = ok ? (G + (int64_t)(k0 + k) * ld + mn0 + mn) : G;
-      cp_async8(sm + k * GD_LDM + mn, src, ok);
-    }
+    // keep the loop-invariant state in registers: without this the compiler re-derives okm / soff from
+    // %ctaid / %tid inside the k-loop (rematerialisation), ~100 extra instructions per slab
+    asm volatile("" : "+r"(okm), "+r"(soff));
   }
-}
+  // copy the NEXT slab into `sm` and advance.  A masked-off copy passes its (possibly out-of-range) address with
+  // src-size 0: nothing is read, the destination is zero-filled.
+  __device__ __forceinline__ void load_next(double* sm) {
+    const double* q = p;
+    double* d = sm + soff;
+    // validity of the 8 copies in one mask: rows/cols from okm, k from kleft (all-ones except in the last slab)
+    unsigned m = okm;
+    if (KCONTIG) {
+      if (kleft <= 0) m = 0;
+    } else if (kleft < 2 * NCOPY) {
+      const int nv = kleft <= 0 ? 0 : (kleft + 1) / 2;  // copies i with 2 i < kleft
+      m &= (1u << nv) - 1u;
+    }
+#pragma unroll
+    for (int i = 0; i < NCOPY; ++i) {
+      cp_async8(d + i * DSTEP, q, (m >> i) & 1u);
+      q += gstep;
+    }
+    p += kstep;
+    kleft -= GD_BK;
+  }
+};
 
 template <bool A_KCONTIG, bool B_KCONTIG>
 __global__ void __launch_bounds__(GD_THREADS) gemm_dmma_kernel(const GemmDesc* __restrict__ descs, const int* info) {
@@ -112,12 +150,16 @@ __global__ void __launch_bounds__(GD_THREADS) gemm_dmma_kernel(const GemmDesc* _
     for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
   const int nk = (d.K + GD_BK - 1) / GD_BK;
+  GdLoader<A_KCONTIG> ldA;
+  GdLoader<B_KCONTIG> ldB;
+  ldA.init(d.A, d.lda, m0, d.M, d.K);
+  ldB.init(d.B, d.ldb, n0, d.N, d.K);
   // prologue
 #pragma unroll
   for (int s = 0; s < GD_STAGES - 1; ++s) {
     if (s < nk) {
-      gd_load_tile<A_KCONTIG>(sA + s * GD_TILE_ELEMS, d.A, d.lda, m0, d.M, s * GD_BK, d.K);
-      gd_load_tile<B_KCONTIG>(sB + s * GD_TILE_ELEMS, d.B, d.ldb, n0, d.N, s * GD_BK, d.K);
+      ldA.load_next(sA + s * GD_TILE_ELEMS);
+      ldB.load_next(sB + s * GD_TILE_ELEMS);
     }
     cp_async_commit();
   }
@@ -128,8 +170,8 @@ __global__ void __launch_bounds__(GD_THREADS) gemm_dmma_kernel(const GemmDesc* _
       const int nxt = kt + GD_STAGES - 1;
       if (nxt < nk) {
         const int s = nxt % GD_STAGES;
-        gd_load_tile<A_KCONTIG>(sA + s * GD_TILE_ELEMS, d.A, d.lda, m0, d.M, nxt * GD_BK, d.K);
-        gd_load_tile<B_KCONTIG>(sB + s * GD_TILE_ELEMS, d.B, d.ldb, n0, d.N, nxt * GD_BK, d.K);
+        ldA.load_next(sA + s * GD_TILE_ELEMS);
+        ldB.load_next(sB + s * GD_TILE_ELEMS);
       }
       cp_async_commit();
     }

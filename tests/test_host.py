@@ -113,3 +113,70 @@ def test_gp_bookkeeping_without_device():
         h.apply_sqrt(np.zeros(3))
     st = pickle.loads(pickle.dumps(h))
     assert not st.computed
+
+
+def test_matrix_free_entry_points_validate_shapes_before_touching_the_device():
+    """KernelInterface.matvec / gradient_contract: argument checks are host-side (same exception types as the rest of
+    the interface, kernel_interface.cpp:51); with valid arguments and no GPU the call must raise, never compute."""
+    from george_b200 import kernels as K, _lib
+    from george_b200._spec import DimensionMismatch
+    k = 1.0 * K.Matern32Kernel(1.0, ndim=2)
+    ki = k.kernel
+    x1, x2 = np.zeros((5, 2)), np.zeros((7, 2))
+    with pytest.raises(DimensionMismatch):
+        ki.matvec(x1, x2, np.zeros(6))                      # v does not match x2
+    with pytest.raises(DimensionMismatch):
+        ki.matvec(x1, np.zeros((7, 3)), np.zeros(7))        # wrong input dimension
+    with pytest.raises(DimensionMismatch):
+        ki.matvec(x1, x2, np.zeros(7), diag=np.zeros(5))    # a diagonal term needs a square operator
+    with pytest.raises(ValueError):
+        ki.matvec(np.zeros(5), x2, np.zeros(7))             # 1-D coordinates
+    with pytest.raises(DimensionMismatch):
+        ki.gradient_contract(np.ones(ki.size, dtype=np.uint32), x1, np.zeros((5, 4)))
+    with pytest.raises(DimensionMismatch):
+        ki.gradient_contract(np.ones(ki.size + 1, dtype=np.uint32), x1, np.zeros((5, 5)))
+    if _lib.load().bgp_device_count() == 0:
+        with pytest.raises(_lib.BGPError):
+            ki.matvec(x1, x2, np.zeros(7))
+        with pytest.raises(_lib.BGPError):
+            ki.gradient_contract(np.ones(ki.size, dtype=np.uint32), x1, np.zeros((5, 5)))
+
+
+def test_grad_log_likelihood_uses_solver_grad_terms_and_falls_back():
+    """GP.grad_log_likelihood composes the gradient from `solver.grad_terms` when the plug-in offers it, and from
+    `get_inverse` + `KernelInterface.gradient_contract` otherwise (reference gp.py:406-468 semantics either way)."""
+    import george_b200 as george
+    from george_b200 import kernels as K
+
+    calls = []
+
+    class FakeSolver(object):
+        def __init__(self, kernel, **kw):
+            self.kernel = kernel
+            self.computed = False
+            self.log_determinant = 0.0
+
+        def compute(self, x, yerr):
+            self.n = len(x)
+            self.computed = True
+
+        def apply_inverse(self, y, in_place=False):
+            return np.array(y, dtype=float)
+
+        def grad_terms(self, r, which):
+            calls.append(("grad_terms", which.copy()))
+            return np.asarray(r, dtype=float), np.arange(1.0, which.size + 1.0), np.full(self.n, 2.0)
+
+    kernel = 2.0 * K.ExpSquaredKernel(1.0)
+    kernel.freeze_parameter("k1:log_constant")
+    gp = george.GP(kernel, solver=FakeSolver, white_noise=np.log(0.1), fit_white_noise=True, mean=0.5, fit_mean=True)
+    x = np.linspace(0, 1, 6)
+    y = np.sin(x)
+    gp.compute(x, 0.1)
+    g = gp.grad_log_likelihood(y)
+    assert calls and list(calls[0][1]) == [0, 1]            # the frozen constant is masked out
+    names = gp.get_parameter_names()
+    assert len(g) == len(names) == 3
+    assert np.isclose(g[0], np.sum(y - 0.5))                # mean: dmu . alpha with alpha = r
+    assert np.isclose(g[1], 0.5 * 0.1 * 2.0 * 6)            # white noise: 0.5 sum(exp(wn) diagA)
+    assert np.isclose(g[2], 0.5 * 2.0)                      # kernel: 0.5 * g[mask] -> entry 1 of (1, 2)
