@@ -26,8 +26,10 @@ int fill_identity_launch(double* A, int64_t n, cudaStream_t s);
 
 constexpr int DN_NB = 64;   // inner panel width (diagonal block in shared memory)
 constexpr int DN_MB = 256;  // middle block of the delayed-update hierarchy (see dense_potrf)
-constexpr int DN_OB = 1024; // outer block: trailing updates beyond it run with K = 1024 on the tensor pipe (measured on
-                            // config 4: 256 -> 556 ms, 512 -> 512 ms, 1024 -> 497 ms; the epilogue of a tile is amortised over K)
+constexpr int DN_OB = 2048; // outer block: trailing updates beyond it run with K = 2048 on the tensor pipe.  Measured on
+                            // config 4 (N = 32768): two levels 256 -> 556 ms, 512 -> 512 ms, 1024 -> 497 ms; three levels
+                            // (64 | 256 | OB) with the slimmer GEMM loader: 1024 -> 419.7 ms, 2048 -> 412.9 ms
+                            // (profiles/dense_cfg4_r01_v5_ob_sweep.txt, dense_cfg4_r01_v7.txt)
 
 // ---- diagonal block Cholesky (NB x NB): one thread per ROW, the row lives in registers ------------------------------
 // Right-looking, fully unrolled: at step k every thread scales its entry of column k and applies the rank-1 update to
