@@ -382,11 +382,18 @@ def run_ours(args):
             try:
                 xs, yerrs, ys = make_data(ns)
                 chk = Native()
-                chk.compute(kernel, xs[:, None], yerrs, wl["min_size"], wl["tol"], 42, rng_mode="reference", exhaust="dense")
-                ll_gpu = -0.5 * (ns * np.log(2 * np.pi) + chk.log_determinant) - 0.5 * chk.dot_solve(ys)
+                t_same = None
+                for _ in range(2):  # second pass: buffers and capacities are warm, as in the timed legs
+                    t0 = time.perf_counter()
+                    chk.compute(kernel, xs[:, None], yerrs, wl["min_size"], wl["tol"], 42, rng_mode="reference", exhaust="dense")
+                    ll_gpu = -0.5 * (ns * np.log(2 * np.pi) + chk.log_determinant) - 0.5 * chk.dot_solve(ys)
+                    t_same = time.perf_counter() - t0
                 line["parity"] = {"n": ns, "mode": "rng_mode=reference, exhaust=dense (the reference algorithm)",
                                   "log_likelihood_gpu": ll_gpu, "log_likelihood_cpu": cb["log_likelihood"],
-                                  "rel_err": abs(ll_gpu - cb["log_likelihood"]) / abs(cb["log_likelihood"]), "bar": 1e-6}
+                                  "rel_err": abs(ll_gpu - cb["log_likelihood"]) / abs(cb["log_likelihood"]), "bar": 1e-6,
+                                  # the SAME algorithm on the SAME sample, host inputs, wall clock: the like-for-like ratio
+                                  "gpu_seconds_same_algorithm": t_same, "cpu_seconds": cb["seconds"],
+                                  "speedup_same_algorithm_same_n": cb["seconds"] / t_same}
             except Exception as exc:  # the check must never cost the bench line
                 line["parity"] = {"n": ns, "error": repr(exc)}
     print(json.dumps(line))
