@@ -54,6 +54,8 @@ def test_matvec_shapes_and_diag(gpu, oracle, n1, n2):
     v = rng.normal(size=n2)
     out = kernel.matvec(x1, x2, v)
     assert np.all(np.abs(out - Km @ v) <= 1e-12 * (np.abs(Km) @ np.abs(v)))
+    if n2 > 5000:   # the square check below builds an n2 x n2 matrix on the CPU
+        return
     # square operator with a diagonal term: (K + diag) v
     d = rng.uniform(0.1, 1.0, n2)
     Ks = oracle.value_symmetric(flatten(kernel), x2)
