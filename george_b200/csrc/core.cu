@@ -171,8 +171,12 @@ int build_dev_program(const bgp_kernel_spec_t* s, DevProgram* P) {
     else fast = (kt == BGP_K_EXP_SINE2 || kt == BGP_K_COSINE || kt == BGP_K_CONSTANT);
   }
   P->flags = fast ? 1 : 0;
-  // program shape:  [S]  or  [Constant, S, *] / [S, Constant, *]  with S in {ExpSquared, Matern32, Matern52, Exp}
-  P->shape = BGP_SHAPE_GENERIC; P->sc = 1.0; P->sm = 1.0;
+  // program shape.  One-term: [S] or [Constant, S, *] / [S, Constant, *] with S in {ExpSquared, Matern32, Matern52, Exp}.
+  // Two-term (1-D quasi-periodic models), T = S | Constant S * | S Constant *  and  E = ExpSine2 | Constant E * | ...:
+  //   T E +  (either order)          ->  c*S + c2*E
+  //   T ExpSine2 *                   ->  (c*S) * E      (the association `c * S * E` produces; other groupings round
+  //                                                      differently and stay on the interpreter)
+  P->shape = BGP_SHAPE_GENERIC; P->sc = 1.0; P->sm = 1.0; P->sc2 = 1.0; P->sg = 0.0; P->sw = 0.0;
   if (fast) {
     auto shape_of = [](int kt) {
       switch (kt) {
@@ -183,13 +187,47 @@ int build_dev_program(const bgp_kernel_spec_t* s, DevProgram* P) {
         default: return 0;
       }
     };
-    if (P->n_nodes == 1 && shape_of(P->leaf[0].kernel_type)) {
-      P->shape = shape_of(P->leaf[0].kernel_type); P->sm = P->leaf[0].mvec[0]; P->sc = 1.0;
-    } else if (P->n_nodes == 3 && P->code[2] == -2 && nl == 2) {
-      const DevLeaf& a = P->leaf[0];
-      const DevLeaf& b = P->leaf[1];
-      if (a.kernel_type == BGP_K_CONSTANT && shape_of(b.kernel_type)) { P->shape = shape_of(b.kernel_type); P->sc = a.rp[0]; P->sm = b.mvec[0]; }
-      else if (b.kernel_type == BGP_K_CONSTANT && shape_of(a.kernel_type)) { P->shape = shape_of(a.kernel_type); P->sc = b.rp[0]; P->sm = a.mvec[0]; }
+    // a "scaled leaf" starting at code position pos: returns the number of code entries it spans (0 = no match)
+    struct Term { int leaf = -1; double c = 1.0; };
+    auto parse_term = [&](int pos, Term* t) -> int {
+      if (pos >= P->n_nodes || P->code[pos] < 0) return 0;
+      const int l0 = P->code[pos];
+      if (pos + 2 < P->n_nodes && P->code[pos + 1] >= 0 && P->code[pos + 2] == -2) {
+        const int l1 = P->code[pos + 1];
+        const bool c0 = P->leaf[l0].kernel_type == BGP_K_CONSTANT, c1 = P->leaf[l1].kernel_type == BGP_K_CONSTANT;
+        if (c0 && !c1) { t->leaf = l1; t->c = P->leaf[l0].rp[0]; return 3; }
+        if (c1 && !c0) { t->leaf = l0; t->c = P->leaf[l1].rp[0]; return 3; }
+      }
+      if (P->leaf[l0].kernel_type == BGP_K_CONSTANT) return 0;
+      t->leaf = l0; t->c = 1.0;
+      return 1;
+    };
+    Term t0, t1;
+    const int n0 = parse_term(0, &t0);
+    if (n0 && n0 == P->n_nodes && shape_of(P->leaf[t0.leaf].kernel_type)) {
+      P->shape = shape_of(P->leaf[t0.leaf].kernel_type); P->sc = t0.c; P->sm = P->leaf[t0.leaf].mvec[0];
+    } else if (n0) {
+      const int n1 = parse_term(n0, &t1);
+      const bool closes = n1 && n0 + n1 + 1 == P->n_nodes;
+      if (closes) {
+        const int op = P->code[n0 + n1];
+        const DevLeaf& a = P->leaf[t0.leaf];
+        const DevLeaf& b = P->leaf[t1.leaf];
+        const int sa = shape_of(a.kernel_type), sb = shape_of(b.kernel_type);
+        const bool ea = a.kernel_type == BGP_K_EXP_SINE2, eb = b.kernel_type == BGP_K_EXP_SINE2;
+        auto two = [&](const Term& ts, const DevLeaf& S, int sshape, const Term& te, const DevLeaf& E, bool sum) {
+          if (sshape != BGP_SHAPE_EXPSQ && sshape != BGP_SHAPE_M32) return;
+          P->shape = sum ? (sshape == BGP_SHAPE_EXPSQ ? BGP_SHAPE_SUM_EXPSQ_ES2 : BGP_SHAPE_SUM_M32_ES2)
+                         : (sshape == BGP_SHAPE_EXPSQ ? BGP_SHAPE_PROD_EXPSQ_ES2 : BGP_SHAPE_PROD_M32_ES2);
+          P->sc = ts.c; P->sm = S.mvec[0]; P->sc2 = te.c; P->sg = E.p[0]; P->sw = E.rp[0];
+        };
+        if (op == -1) {  // sum: commutative, either order
+          if (sa && eb) two(t0, a, sa, t1, b, true);
+          else if (ea && sb) two(t1, b, sb, t0, a, true);
+        } else if (op == -2 && n1 == 1) {  // (c*S) * E  or  (c*E) * S is NOT the same rounding: only the first form
+          if (sa && eb) two(t0, a, sa, t1, b, false);
+        }
+      }
     }
   }
   return BGP_OK;

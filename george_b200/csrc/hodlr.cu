@@ -92,8 +92,8 @@ struct bgp_hodlr {
   DevBuf<int> d_work_count;
   bool profile = false;
   std::vector<cudaEvent_t> prof_events;
-  double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  DevBuf<double> d_vpart, d_upart;
+  double prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // see bgp_hodlr_last_aca_profile
+  DevBuf<double> d_vpart, d_upart, d_vmax;
   int aca_iters = 0;
   size_t w_cap = 0;
 
@@ -278,11 +278,13 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   BGP_TRY(h->d_cand_k.reserve((size_t)cand_total, s));
   BGP_TRY(h->d_cand_words.reserve((size_t)cand_total, s));
   BGP_TRY(h->d_cmax.reserve((size_t)cand_total, s));
-  BGP_TRY(h->d_epart.reserve((size_t)std::max(ncc, 1), s));
+  BGP_TRY(h->d_epart.reserve((size_t)std::max(ncc, 1) * A2_NSUB, s));
   BGP_TRY(h->d_cchunk_node.reserve(ncc, s));
   BGP_TRY(h->d_rchunk_node.reserve(nrc, s));
-  BGP_TRY(h->d_vpart.reserve((size_t)ncc * (capmax + 1), s));
-  BGP_TRY(h->d_upart.reserve((size_t)nrc * (capmax + 1), s));
+  BGP_TRY(h->d_vpart.reserve((size_t)ncc * A2_NSUB * (capmax + 1), s));
+  BGP_TRY(h->d_upart.reserve((size_t)nrc * A2_NSUB * (capmax + 1), s));
+  const bool cull = shape_has_bound(h->prog.shape) && !getenv("BGP_NO_CULL");  // BGP_NO_CULL: exhaustive scan (tests compare both)
+  if (cull) BGP_TRY(h->d_vmax.reserve((size_t)ncc * A2_NGROUP * capmax, s));
   BGP_TRY(h->d_nactive.reserve(2, s));
   int n_top = 0;
   for (int i = 0; i < nn; ++i) n_top += hn[i].is_top;
@@ -303,6 +305,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   a.idx_ws = h->d_idx.p; a.piv_rows = h->d_piv_rows.p; a.piv_cols = h->d_piv_cols.p;
   a.cand = h->d_cand.p; a.cand_k = h->d_cand_k.p; a.cand_words = h->d_cand_words.p; a.cmax = h->d_cmax.p; a.epart = h->d_epart.p;
   a.cchunk_node = h->d_cchunk_node.p; a.rchunk_node = h->d_rchunk_node.p; a.vpart = h->d_vpart.p; a.upart = h->d_upart.p;
+  a.vmax = cull ? h->d_vmax.p : nullptr;
   a.capmax = capmax; a.n_active = h->d_nactive.p; a.stats = h->d_stats.p;
   a.work = h->d_work.p; a.work_count = h->d_work_count.p; a.work_cap = (int)work_cap; a.iter = -1;
   a.shard_rank = dist_top ? h->opts.shard_rank : 0; a.shard_count = dist_top ? h->opts.shard_count : 1;
@@ -319,31 +322,42 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   int active = nn, iters = 0;
   const int eval_grid = num_sms() * 6;  // persistent CTAs over the work list (2-3 resident per SM, a few rounds)
   bool top_active = dist_top && n_top > 0;  // identical on every rank: the top nodes take identical decisions
+  // profiling: 7 events per lock-step iteration (before eval, then after each of the six kernels)
+  constexpr int PE = 7;
+  auto prof_mark = [&](int it, int slot) -> int {
+    if (!h->profile) return BGP_OK;
+    const size_t need = (size_t)PE * (it + 1);
+    while (h->prof_events.size() < need) {
+      cudaEvent_t e;
+      BGP_CUDA(cudaEventCreate(&e));
+      h->prof_events.push_back(e);
+    }
+    BGP_CUDA(cudaEventRecord(h->prof_events[(size_t)PE * it + slot], s));
+    return BGP_OK;
+  };
   while (active > 0) {
     for (int rep = 0; rep < 8; ++rep) {
-      if (h->profile) {
-        if (h->prof_events.size() < (size_t)(2 * (iters + 1))) {
-          cudaEvent_t e0, e1;
-          BGP_CUDA(cudaEventCreate(&e0)); BGP_CUDA(cudaEventCreate(&e1));
-          h->prof_events.push_back(e0); h->prof_events.push_back(e1);
-        }
-        BGP_CUDA(cudaEventRecord(h->prof_events[2 * iters], s));
-      }
+      BGP_TRY(prof_mark(iters, 0));
       a.iter = iters;
       a2_eval_launch(h->prog.shape, dim3(eval_grid), s, a);
-      if (h->profile) BGP_CUDA(cudaEventRecord(h->prof_events[2 * iters + 1], s));
-      if (top_active) BGP_TRY(comm_allreduce_max_u64(h->d_cmax.p, (size_t)top_cand_total, s));
       BGP_LAUNCH_CHECK();
+      if (top_active) BGP_TRY(comm_allreduce_max_u64(h->d_cmax.p, (size_t)top_cand_total, s));
+      BGP_TRY(prof_mark(iters, 1));
       a2_decide_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), s>>>(a);
       BGP_LAUNCH_CHECK();
-      a2_vrow_kernel<<<ncc, A2_THREADS, 0, s>>>(a);
+      BGP_TRY(prof_mark(iters, 2));
+      a2_vrow_launch(h->prog.shape, dim3(ncc, A2_NSUB), s, a);
       BGP_LAUNCH_CHECK();
+      BGP_TRY(prof_mark(iters, 3));
       a2_pivot_kernel<<<nn, 32, 0, s>>>(a);
       BGP_LAUNCH_CHECK();
-      a2_vnorm_ucol_kernel<<<ncc + nrc, A2_THREADS, 0, s>>>(a, ncc);
+      BGP_TRY(prof_mark(iters, 4));
+      a2_vnorm_ucol_launch(h->prog.shape, dim3(ncc + nrc, A2_NSUB), s, a, ncc);
       BGP_LAUNCH_CHECK();
+      BGP_TRY(prof_mark(iters, 5));
       a2_finish_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), s>>>(a);
       BGP_LAUNCH_CHECK();
+      BGP_TRY(prof_mark(iters, 6));
       iters++;
     }
     int act2[2] = {0, 0};
@@ -359,10 +373,17 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
     BGP_CUDA(cudaMemcpyAsync(st4, h->d_stats.p, sizeof(st4), cudaMemcpyDeviceToHost, s));
     BGP_CUDA(cudaStreamSynchronize(s));
     h->prof[1] = iters; h->prof[2] = (double)st4[0]; h->prof[3] = (double)st4[1]; h->prof[4] = (double)st4[2];
+    h->prof[5] = (double)st4[3];
     if (h->profile) {
-      double tot = 0.0;
-      for (int i = 0; i < iters; ++i) { float ms = 0; cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]); tot += ms; }
-      h->prof[0] = tot;
+      double tot[6] = {0, 0, 0, 0, 0, 0};
+      for (int i = 0; i < iters; ++i)
+        for (int k = 0; k < 6; ++k) {
+          float ms = 0;
+          cudaEventElapsedTime(&ms, h->prof_events[(size_t)PE * i + k], h->prof_events[(size_t)PE * i + k + 1]);
+          tot[k] += ms;
+        }
+      h->prof[0] = tot[0];
+      for (int k = 0; k < 6; ++k) h->prof[6 + k] = tot[k];
     }
   }
   if (h->opts.exhaust_mode == BGP_EXHAUST_DENSE) {
@@ -622,6 +643,7 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
   std::vector<int> ncols_by_depth(max_depth + 2, rtot);
   for (int dpt = 0; dpt <= max_depth + 1; ++dpt) ncols_by_depth[dpt] = dpt < nlev ? h->levels[dpt].ucol : rtot;
 
+  BGP_CUDA(cudaEventRecord(h->ev[6], sA));  // ranks known, both streams drained up to here: the up-sweep starts
   BGP_TRY(h->d_nodes.reserve(std::max(ndesc, 1), sA));
   BGP_TRY(h->d_node_logdet.reserve(std::max(ndesc, 1), sA));
   BGP_TRY(h->d_U.reserve((size_t)n * std::max(rtot, 1), sA));
@@ -677,7 +699,7 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->t_ms[0] = ms;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]); h->t_ms[1] = ms;
-  cudaEventElapsedTime(&ms, h->ev[1], h->ev[3]); h->t_ms[2] = ms;
+  cudaEventElapsedTime(&ms, h->ev[6], h->ev[3]); h->t_ms[2] = ms;  // panel finalisation + leaf solves + level sweeps only
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]); h->t_ms[3] = ms;
 
   // algorithmic work
@@ -745,7 +767,7 @@ void bgp_hodlr_destroy(bgp_hodlr_t* h) {
   h->d_a2nodes.release(); h->d_a2states.release(); h->d_epart.release(); h->d_cand.release(); h->d_cand_k.release();
   h->d_cand_words.release(); h->d_cchunk_node.release(); h->d_rchunk_node.release(); h->d_nactive.release();
   h->d_inv.release(); h->d_gscratch.release(); h->d_which.release();
-  h->d_vpart.release(); h->d_upart.release(); h->d_cmax.release(); h->d_stats.release(); h->d_work.release(); h->d_work_count.release();
+  h->d_vpart.release(); h->d_upart.release(); h->d_vmax.release(); h->d_cmax.release(); h->d_stats.release(); h->d_work.release(); h->d_work_count.release();
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   if (h->sA) {
     cudaStreamSynchronize(h->sA); cudaStreamSynchronize(h->sB);
@@ -913,9 +935,9 @@ int bgp_hodlr_set_profiling(bgp_hodlr_t* h, int on) {
   h->profile = on != 0;
   return BGP_OK;
 }
-int bgp_hodlr_last_aca_profile(const bgp_hodlr_t* h, double* p5) {
+int bgp_hodlr_last_aca_profile(const bgp_hodlr_t* h, double* p12) {
   if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
-  for (int i = 0; i < 5; ++i) p5[i] = h->prof[i];
+  for (int i = 0; i < 12; ++i) p12[i] = h->prof[i];
   return BGP_OK;
 }
 int bgp_hodlr_last_work(const bgp_hodlr_t* h, double* w6) {

@@ -28,6 +28,10 @@ constexpr int A2_EPT = A2_CHUNK / A2_THREADS;  // elements per thread
 constexpr int A2_CG = 4;          // candidates evaluated together (register blocking)
 constexpr int A2_ITEM_CB = 8;      // candidate blocks (of A2_CG rows) per eval work item
 constexpr int A2_BMAX = 4096;     // max speculative candidates per iteration
+constexpr int A2_NSUB = 4;        // the residual kernels (vrow / ucol / vnorm) split a chunk into sub-chunks of A2_THREADS
+constexpr int A2_GROUP = A2_CHUNK / (A2_THREADS / 32);  // 128 columns: what one warp of a2_eval sweeps (bound granularity)
+constexpr int A2_NGROUP = A2_CHUNK / A2_GROUP;           // 8 groups per chunk
+static_assert(A2_NSUB * A2_THREADS == A2_CHUNK, "sub-chunks tile a chunk");
 constexpr int A2_HASH = 8192;     // open-addressing slots of the swap-pop overlay (>= 2 * A2_BMAX)
 
 struct A2Node {  // static description
@@ -278,11 +282,13 @@ struct A2Args {
   int* cand_k;     // drawn positions
   int* cand_words; // cumulative words
   unsigned long long* cmax;  // per candidate: bit pattern of max |residual| over all chunks (atomicMax)
-  A2EPart* epart;  // one slot per column chunk: arg-max of the winning row's residual in that chunk
+  A2EPart* epart;  // one slot per column sub-chunk: arg-max of the winning row's residual there
   const int* cchunk_node;  // chunk -> node
   const int* rchunk_node;
-  double* vpart;   // per column chunk: [chunk * (capmax + 1)] : vn2 then dots[k]
-  double* upart;   // per row chunk
+  double* vpart;   // per column sub-chunk: [(chunk * A2_NSUB + sub) * (capmax + 1)] : vn2 then dots[k]
+  double* upart;   // per row sub-chunk
+  double* vmax;    // per (column chunk, 128-column group, factor k): max |V(j, k)| over the group  [(chunk*8+g)*capmax + k]
+                   // (bound culling of a2_eval; nullptr when the program has no distance bound)
   int capmax;
   int* n_active;
   int4* work;          // eval work items (chunk, first candidate, #candidates, node), two buffers of work_cap
@@ -290,7 +296,8 @@ struct A2Args {
   int work_cap;
   int iter;            // lock-step iteration number (selects the buffers)
   int shard_rank, shard_count;  // multi-GPU: top nodes' column chunks are dealt round-robin to the ranks
-  unsigned long long* stats;  // [0] candidate-row kernel evaluations, [1] residual-update FMAs, [2] candidates, [3] accepted
+  unsigned long long* stats;  // [0] candidate-row entries verified (pairs), [1] residual-update FMAs executed, [2] candidates,
+                              // [3] entries actually evaluated by a2_eval (the rest were bounded < 1e-14 without evaluation)
 };
 
 // ---- init: index list, RNG seed, first candidates -------------------------------------------------------------
@@ -322,13 +329,23 @@ __global__ void __launch_bounds__(A2_THREADS) a2_init_kernel(A2Args a) {
 // Warp-autonomous: each warp owns 128 columns of the chunk (4 per lane, coalesced) and walks the candidate rows in
 // blocks of A2_CG with no block-level synchronisation and no shared memory: the candidate's coordinates and its U row
 // are warp-uniform (broadcast) loads, the arg-max is a shuffle reduction and one atomicMax per (candidate, warp).
-template <class KFn>
+//
+// Bound culling (CULL; 1-D inputs, programs whose |k| has a decreasing bound in the distance).  The only consumer of the
+// maxima is the test  max_j |residual(i, j)| >= 1e-14  (hodlr.h:191).  For a candidate row i and this warp's 128 columns
+//     |residual(i, j)| <= |k(x_i, x_j)| + sum_q |U(i, q)| |V(j, q)| <= bound(gap(x_i, group)) + sum_q |U(i, q)| vmax(group, q)
+// and when the right-hand side (with a 1e-6 relative margin for the rounding of both sides) is below 1e-14 the group
+// cannot change the outcome of that test, so it is not evaluated.  Lane c works out the bound of candidate c; the warp
+// then sweeps only the surviving candidates.  The decisions — hence pivots, ranks and RNG draws — are exactly those of
+// the exhaustive scan; what disappears is the O(rows x cols) evaluation of entries that are provably negligible
+// (Matern / squared-exponential tails: everything farther than a few dozen length scales from the block's corner).
+template <class KFn, bool CULL>
 __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, int rank, int chunk, int c_first,
-                                             int c_count, int ndim, KFn fn) {
+                                             int c_count, int ndim, KFn fn, unsigned long long& n_eval,
+                                             unsigned long long& n_fma) {
   const int lc = chunk - nd.cchunk0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int w_lo = lc * A2_CHUNK + warp * (A2_CHUNK / (A2_THREADS / 32));  // first column of this warp
-  const int w_n = min(A2_CHUNK / (A2_THREADS / 32), nd.n_cols - w_lo);
+  const int w_lo = lc * A2_CHUNK + warp * A2_GROUP;  // first column of this warp
+  const int w_n = min(A2_GROUP, nd.n_cols - w_lo);
   if (w_n <= 0) return;
   const double* Vcols = a.Vp + (int64_t)nd.vcol * a.ld;
   const double* xr = a.x + (int64_t)nd.row0 * ndim;
@@ -339,55 +356,106 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
 #pragma unroll
   for (int e = 0; e < A2_EPT; ++e) ncol[e] = min(lane + 32 * e, w_n - 1);  // clamped (masked in the arg-max)
 
+  double glo = 0.0, ghi = 0.0;
+  const double* vmaxg = nullptr;
+  if constexpr (CULL) {
+    glo = __longlong_as_double(0x7ff0000000000000ll); ghi = -glo;
+#pragma unroll
+    for (int e = 0; e < A2_EPT; ++e) { const double xv = xc[ncol[e]]; glo = fmin(glo, xv); ghi = fmax(ghi, xv); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      glo = fmin(glo, __shfl_xor_sync(0xffffffffu, glo, o));
+      ghi = fmax(ghi, __shfl_xor_sync(0xffffffffu, ghi, o));
+    }
+    vmaxg = a.vmax + ((int64_t)chunk * A2_NGROUP + warp) * a.capmax;
+  }
+
   const int ncand = c_first + c_count;
-  for (int cb = c_first; cb < ncand; cb += A2_CG) {
-    const int ncb = min(A2_CG, ncand - cb);
-    int row[A2_CG];
-#pragma unroll
-    for (int c = 0; c < A2_CG; ++c) row[c] = cand[cb + min(c, ncb - 1)];
-    double vals[A2_CG][A2_EPT];
-#pragma unroll
-    for (int e = 0; e < A2_EPT; ++e) {
-      const double* x2 = xc + (int64_t)ncol[e] * ndim;
-#pragma unroll
-      for (int c = 0; c < A2_CG; ++c) vals[c][e] = fn(xr + (int64_t)row[c] * ndim, x2);
+  for (int cb0 = c_first; cb0 < ncand; cb0 += 32) {
+    const int myc = cb0 + lane;
+    const bool valid = myc < ncand;
+    const int myrow = valid ? cand[myc] : 0;
+    unsigned live = __ballot_sync(0xffffffffu, valid);
+    if constexpr (CULL) {
+      bool keep = valid;
+      if (valid) {
+        const double xi = xr[myrow];
+        const double gap = fmax(0.0, fmax(glo - xi, xi - ghi));
+        double b = fn.bound(gap);
+        for (int k = 0; k < rank; ++k) b += fabs(__ldcg(Vcols + (int64_t)k * a.ld + nd.row0 + myrow)) * vmaxg[k];
+        keep = !(b * 1.000001 < 1e-14);  // NaN keeps the candidate
+      }
+      live = __ballot_sync(0xffffffffu, keep);
     }
-    for (int k = 0; k < rank; ++k) {
-      const double* vcol = Vcols + (int64_t)k * a.ld;
-      double vk[A2_EPT], u[A2_CG];
+    n_eval += (unsigned long long)__popc(live) * (unsigned long long)w_n;
+    n_fma += (unsigned long long)__popc(live) * (unsigned long long)w_n * (unsigned long long)rank;
+    while (live) {
+      int sel[A2_CG], row[A2_CG];
+      int ncb = 0;
 #pragma unroll
-      for (int c = 0; c < A2_CG; ++c) u[c] = __ldcg(vcol + nd.row0 + row[c]);
-#pragma unroll
-      for (int e = 0; e < A2_EPT; ++e) vk[e] = vcol[nd.col0 + w_lo + ncol[e]];
-#pragma unroll
-      for (int c = 0; c < A2_CG; ++c)
-#pragma unroll
-        for (int e = 0; e < A2_EPT; ++e) vals[c][e] -= u[c] * vk[e];
-    }
-#pragma unroll
-    for (int c = 0; c < A2_CG; ++c) {
-      double best = 0.0;
-      bool isnan_any = false;
+      for (int c = 0; c < A2_CG; ++c) {
+        if (live) { sel[c] = __ffs(live) - 1; live &= live - 1; ncb = c + 1; }
+        else sel[c] = sel[0];
+        row[c] = __shfl_sync(0xffffffffu, myrow, sel[c]);
+      }
+      double vals[A2_CG][A2_EPT];
 #pragma unroll
       for (int e = 0; e < A2_EPT; ++e) {
-        const double av = fabs(vals[c][e]);
-        if (lane + 32 * e < w_n) { best = fmax(best, av); isnan_any |= (av != av); }
-      }
-      if (isnan_any) best = __longlong_as_double(0x7ff8000000000000ll);
-      unsigned long long bits = (unsigned long long)__double_as_longlong(best);
+        const double* x2 = xc + (int64_t)ncol[e] * ndim;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long ob = __shfl_xor_sync(0xffffffffu, bits, o);
-        bits = ob > bits ? ob : bits;
+        for (int c = 0; c < A2_CG; ++c) vals[c][e] = fn(xr + (int64_t)row[c] * ndim, x2);
       }
-      if (lane == 0 && c < ncb) atomicMax(cmax + cb + c, bits);
+      int k = 0;
+      for (; k + 2 <= rank; k += 2) {  // two factor columns per trip: the loads of the second overlap the FMAs of the first
+        const double* vc0 = Vcols + (int64_t)k * a.ld;
+        const double* vc1 = vc0 + a.ld;
+        double vk0[A2_EPT], vk1[A2_EPT], u0[A2_CG], u1[A2_CG];
+#pragma unroll
+        for (int c = 0; c < A2_CG; ++c) { u0[c] = __ldcg(vc0 + nd.row0 + row[c]); u1[c] = __ldcg(vc1 + nd.row0 + row[c]); }
+#pragma unroll
+        for (int e = 0; e < A2_EPT; ++e) { vk0[e] = vc0[nd.col0 + w_lo + ncol[e]]; vk1[e] = vc1[nd.col0 + w_lo + ncol[e]]; }
+#pragma unroll
+        for (int c = 0; c < A2_CG; ++c)
+#pragma unroll
+          for (int e = 0; e < A2_EPT; ++e) { vals[c][e] -= u0[c] * vk0[e]; vals[c][e] -= u1[c] * vk1[e]; }
+      }
+      for (; k < rank; ++k) {
+        const double* vcol = Vcols + (int64_t)k * a.ld;
+        double vk[A2_EPT], u[A2_CG];
+#pragma unroll
+        for (int c = 0; c < A2_CG; ++c) u[c] = __ldcg(vcol + nd.row0 + row[c]);
+#pragma unroll
+        for (int e = 0; e < A2_EPT; ++e) vk[e] = vcol[nd.col0 + w_lo + ncol[e]];
+#pragma unroll
+        for (int c = 0; c < A2_CG; ++c)
+#pragma unroll
+          for (int e = 0; e < A2_EPT; ++e) vals[c][e] -= u[c] * vk[e];
+      }
+#pragma unroll
+      for (int c = 0; c < A2_CG; ++c) {
+        double best = 0.0;
+        bool isnan_any = false;
+#pragma unroll
+        for (int e = 0; e < A2_EPT; ++e) {
+          const double av = fabs(vals[c][e]);
+          if (lane + 32 * e < w_n) { best = fmax(best, av); isnan_any |= (av != av); }
+        }
+        if (isnan_any) best = __longlong_as_double(0x7ff8000000000000ll);
+        unsigned long long bits = (unsigned long long)__double_as_longlong(best);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long ob = __shfl_xor_sync(0xffffffffu, bits, o);
+          bits = ob > bits ? ob : bits;
+        }
+        if (lane == 0 && c < ncb && bits != 0ull) atomicMax(cmax + cb0 + sel[c], bits);
+      }
     }
   }
 }
 
 // one instantiation per program shape: the specialised ones carry no interpreter and need far fewer registers
 template <int SHAPE>
-__global__ void __launch_bounds__(A2_THREADS, (SHAPE == BGP_SHAPE_GENERIC) ? 2 : 3) a2_eval_kernel(A2Args a) {
+__global__ void __launch_bounds__(A2_THREADS, 2) a2_eval_kernel(A2Args a) {
   __shared__ DevProgram P;
   // persistent CTAs sweep the work list published by the node kernels of the previous step: perfectly balanced over
   // the chip whatever mix of nodes is still active, and no empty CTAs
@@ -399,27 +467,20 @@ __global__ void __launch_bounds__(A2_THREADS, (SHAPE == BGP_SHAPE_GENERIC) ? 2 :
     stage_program(&P, a.prog);
     __syncthreads();
   }
+  const auto fn = ShapeEval<SHAPE>::make(&P, a.prog);
+  constexpr bool CULL = shape_has_bound(SHAPE);
+  unsigned long long n_eval = 0ull, n_fma = 0ull;
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
     const int4 w = items[it];
     const A2Node& nd = a.nodes[w.w];
     const int rank = a.states[w.w].rank;
-    if constexpr (SHAPE == BGP_SHAPE_GENERIC) {
-      GenericKernelFn fn{&P};
-      a2_eval_body(a, nd, rank, w.x, w.y, w.z, P.ndim, fn);
-    } else {
-      ScaledProfile1D<SHAPE> fn{a.prog->sc, a.prog->sm};
-      a2_eval_body(a, nd, rank, w.x, w.y, w.z, 1, fn);
-    }
+    if constexpr (SHAPE == BGP_SHAPE_GENERIC) a2_eval_body<decltype(fn), false>(a, nd, rank, w.x, w.y, w.z, P.ndim, fn, n_eval, n_fma);
+    else a2_eval_body<decltype(fn), CULL>(a, nd, rank, w.x, w.y, w.z, 1, fn, n_eval, n_fma);
   }
+  if ((threadIdx.x & 31) == 0 && n_eval) { atomicAdd(a.stats + 3, n_eval); atomicAdd(a.stats + 1, n_fma); }
 }
 inline void a2_eval_launch(int shape, dim3 grid, cudaStream_t s, const A2Args& a) {
-  switch (shape) {
-    case BGP_SHAPE_EXPSQ: a2_eval_kernel<BGP_SHAPE_EXPSQ><<<grid, A2_THREADS, 0, s>>>(a); break;
-    case BGP_SHAPE_M32: a2_eval_kernel<BGP_SHAPE_M32><<<grid, A2_THREADS, 0, s>>>(a); break;
-    case BGP_SHAPE_M52: a2_eval_kernel<BGP_SHAPE_M52><<<grid, A2_THREADS, 0, s>>>(a); break;
-    case BGP_SHAPE_EXP: a2_eval_kernel<BGP_SHAPE_EXP><<<grid, A2_THREADS, 0, s>>>(a); break;
-    default: a2_eval_kernel<BGP_SHAPE_GENERIC><<<grid, A2_THREADS, 0, s>>>(a); break;
-  }
+  BGP_SHAPE_SWITCH(shape, (a2_eval_kernel<SHAPE><<<grid, A2_THREADS, 0, s>>>(a)));
 }
 
 // ---- decide: first usable candidate wins; commit the RNG / index list up to it ----------------------------------
@@ -440,7 +501,6 @@ __global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
   if (threadIdx.x == 0) {
     s_winner = 0x7fffffff;
     atomicAdd(a.stats + 0, (unsigned long long)ncand * (unsigned long long)nd.n_cols);
-    atomicAdd(a.stats + 1, (unsigned long long)ncand * (unsigned long long)nd.n_cols * (unsigned long long)st.rank);
     atomicAdd(a.stats + 2, (unsigned long long)ncand);
   }
   __syncthreads();
@@ -475,7 +535,9 @@ __global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
       st.n_index -= (p + 1);
       st.piv_i = cand[p];
       st.phase = A2_ACCEPT;  // pivot column / value follow from a2_vrow + a2_pivot
-      st.B = max(1, min(st.B, 2 * (p + 1)));
+      // next batch: as many candidates as this pivot search needed (a kernel whose rows are all usable settles at
+      // ONE candidate per step: every speculative row costs a pass over the factor panel)
+      st.B = max(1, min(st.B, p + 1));
     }
     return;
   }
@@ -497,61 +559,74 @@ __global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
   }
 }
 
-// ---- vrow: residual of the winning row over one column chunk, stored UN-normalised in panel column `rank`, plus the
-//      chunk's arg-max (hodlr.h:186-189).  Every rank does this for every node (it is one row per accepted pivot).
+// ---- residual of one row (vrow) or one column (ucol) of the block over a sub-chunk of A2_THREADS entries ------------
+// One entry per thread; the factor columns are streamed with A2_KU loads in flight per thread and subtracted in the
+// order q = 0, 1, ... (the order of hodlr.h:188 / :199 and of the oracle), so the value does not depend on the schedule.
+constexpr int A2_KU = 8;
+template <class KFn>
+__device__ __forceinline__ double a2_resid_entry(const KFn& fn, const double* xa, const double* xb, int rank,
+                                                 const double* __restrict__ pcol,  // &panel[0][this entry]
+                                                 int64_t ld, const double* __restrict__ coef_g,  // coef[q] = coef_g[q * ld]
+                                                 double* s_coef, bool active) {
+  double val = active ? fn(xa, xb) : 0.0;
+  for (int k0 = 0; k0 < rank; k0 += 128) {
+    const int nk = min(128, rank - k0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < nk; k += A2_THREADS) s_coef[k] = __ldcg(coef_g + (int64_t)(k0 + k) * ld);
+    __syncthreads();
+    if (active) {
+      const double* pc = pcol + (int64_t)k0 * ld;
+      int k = 0;
+      for (; k + A2_KU <= nk; k += A2_KU) {
+        double pv[A2_KU];
+#pragma unroll
+        for (int q = 0; q < A2_KU; ++q) pv[q] = pc[(int64_t)(k + q) * ld];
+#pragma unroll
+        for (int q = 0; q < A2_KU; ++q) val -= s_coef[k + q] * pv[q];
+      }
+      for (; k < nk; ++k) val -= s_coef[k] * pc[(int64_t)k * ld];
+    }
+  }
+  return val;
+}
+
+// ---- vrow: residual of the winning row over one column sub-chunk, stored UN-normalised in panel column `rank`, plus
+//      the sub-chunk's arg-max (hodlr.h:186-189).  Same evaluator as a2_eval (one shape, one arithmetic).
+template <int SHAPE>
 __global__ void __launch_bounds__(A2_THREADS) a2_vrow_kernel(A2Args a) {
   __shared__ DevProgram P;
   __shared__ double s_x[ACA_MAX_NDIM];
   __shared__ double s_u[128];
   __shared__ double s_red[A2_THREADS / 32];
   __shared__ int s_redi[A2_THREADS / 32];
-  const int chunk = blockIdx.x;
+  const int chunk = blockIdx.x, sub = blockIdx.y;
   const int nid = a.cchunk_node[chunk];
   const A2State& st = a.states[nid];
   if (st.phase != A2_ACCEPT || !st.active) return;
   const A2Node nd = a.nodes[nid];
-  stage_program(&P, a.prog);
+  const int lc = chunk - nd.cchunk0;
+  const int c_lo = lc * A2_CHUNK + sub * A2_THREADS;
+  if (c_lo >= nd.n_cols) return;
+  if constexpr (SHAPE == BGP_SHAPE_GENERIC) stage_program(&P, a.prog);
   const int ndim = a.prog->ndim;
   const int rank = st.rank;
-  const int lc = chunk - nd.cchunk0;
-  const int c_lo = lc * A2_CHUNK;
-  const int c_n = min(A2_CHUNK, nd.n_cols - c_lo);
+  const int c_n = min(A2_THREADS, nd.n_cols - c_lo);
   double* Vcols = a.Vp + (int64_t)nd.vcol * a.ld;
-  const double* xc = a.x + (int64_t)(nd.col0 + c_lo) * ndim;
   const int i = st.piv_i;
   for (int q = threadIdx.x; q < ndim; q += A2_THREADS) s_x[q] = a.x[(int64_t)(nd.row0 + i) * ndim + q];
   __syncthreads();
-  double vals[A2_EPT];
-#pragma unroll
-  for (int e = 0; e < A2_EPT; ++e) {
-    const int n = threadIdx.x + e * A2_THREADS;
-    vals[e] = (n < c_n) ? kernel_value(P, s_x, xc + (int64_t)n * ndim) : 0.0;
-  }
-  for (int k0 = 0; k0 < rank; k0 += 128) {
-    const int nk = min(128, rank - k0);
-    __syncthreads();
-    for (int k = threadIdx.x; k < nk; k += A2_THREADS) s_u[k] = __ldcg(Vcols + (int64_t)(k0 + k) * a.ld + nd.row0 + i);
-    __syncthreads();
-#pragma unroll 4
-    for (int k = 0; k < nk; ++k) {
-      const double u = s_u[k];
-#pragma unroll
-      for (int e = 0; e < A2_EPT; ++e) {
-        const int n = threadIdx.x + e * A2_THREADS;
-        if (n < c_n) vals[e] -= u * Vcols[(int64_t)(k0 + k) * a.ld + nd.col0 + c_lo + n];
-      }
-    }
-  }
+  const auto fn = ShapeEval<SHAPE>::make(&P, a.prog);
+  const int n = threadIdx.x;
+  const bool act = n < c_n;
+  const int nn = act ? n : 0;
+  const double val = a2_resid_entry(fn, s_x, a.x + (int64_t)(nd.col0 + c_lo + nn) * ndim, rank, Vcols + nd.col0 + c_lo + nn,
+                                    a.ld, Vcols + nd.row0 + i, s_u, act);
   double best = -1.0, bval = 0.0;
   int bidx = 0x7fffffff;
-#pragma unroll
-  for (int e = 0; e < A2_EPT; ++e) {
-    const int n = threadIdx.x + e * A2_THREADS;
-    if (n < c_n) {
-      Vcols[(int64_t)rank * a.ld + nd.col0 + c_lo + n] = vals[e];
-      const double av = fabs(vals[e]);
-      if (av > best) { best = av; bidx = c_lo + n; bval = vals[e]; }
-    }
+  if (act) {
+    Vcols[(int64_t)rank * a.ld + nd.col0 + c_lo + n] = val;
+    best = fabs(val); bidx = c_lo + n; bval = val;
+    if (val != val) best = __longlong_as_double(0x7ff0000000000000ll);  // a NaN wins the arg-max (it ends the reference's loop)
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -567,15 +642,16 @@ __global__ void __launch_bounds__(A2_THREADS) a2_vrow_kernel(A2Args a) {
     for (int w = 1; w < A2_THREADS / 32; ++w) {
       const double ov = s_red[w];
       const int oi = s_redi[w];
-      if (fabs(ov) > fabs(bval) || (fabs(ov) == fabs(bval) && oi < bidx) || (ov != ov)) { bval = ov; bidx = oi; }
+      if (oi == 0x7fffffff) continue;
+      if (bidx == 0x7fffffff || fabs(ov) > fabs(bval) || (fabs(ov) == fabs(bval) && oi < bidx) || (ov != ov && !(bval != bval))) { bval = ov; bidx = oi; }
     }
     A2EPart p;
     p.val = bval; p.idx = bidx; p._pad = 0;
-    a.epart[nd.cchunk0 + lc] = p;  // one slot per column chunk
+    a.epart[(int64_t)(nd.cchunk0 + lc) * A2_NSUB + sub] = p;
   }
 }
 
-// ---- pivot: arg-max over the chunks of the winning row (first maximum, as Eigen's maxCoeff) ------------------------
+// ---- pivot: arg-max over the sub-chunks of the winning row (first maximum, as Eigen's maxCoeff) ---------------------
 __global__ void __launch_bounds__(32) a2_pivot_kernel(A2Args a) {
   const int nid = blockIdx.x;
   A2State& st = a.states[nid];
@@ -584,47 +660,62 @@ __global__ void __launch_bounds__(32) a2_pivot_kernel(A2Args a) {
   const int lane = threadIdx.x;
   double bval = 0.0;
   int bidx = 0x7fffffff;
-  for (int ch = lane; ch < nd.n_cchunks; ch += 32) {
-    const A2EPart q = a.epart[nd.cchunk0 + ch];
-    if (fabs(q.val) > fabs(bval) || (fabs(q.val) == fabs(bval) && q.idx < bidx) || (q.val != q.val)) { bval = q.val; bidx = q.idx; }
+  const int nsub = (nd.n_cols + A2_THREADS - 1) / A2_THREADS;  // sub-chunks that exist (slot = chunk * A2_NSUB + sub, contiguous)
+  for (int ch = lane; ch < nsub; ch += 32) {
+    const A2EPart q = a.epart[(int64_t)nd.cchunk0 * A2_NSUB + ch];
+    if (q.idx == 0x7fffffff) continue;
+    if (bidx == 0x7fffffff || fabs(q.val) > fabs(bval) || (fabs(q.val) == fabs(bval) && q.idx < bidx) || (q.val != q.val && !(bval != bval))) { bval = q.val; bidx = q.idx; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const double ov = __shfl_xor_sync(0xffffffffu, bval, o);
     const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-    if (fabs(ov) > fabs(bval) || (fabs(ov) == fabs(bval) && oi < bidx) || (ov != ov)) { bval = ov; bidx = oi; }
+    if (oi == 0x7fffffff) continue;
+    if (bidx == 0x7fffffff || fabs(ov) > fabs(bval) || (fabs(ov) == fabs(bval) && oi < bidx) || (ov != ov && !(bval != bval))) { bval = ov; bidx = oi; }
   }
   if (lane == 0) { st.piv_j = bidx; st.pivot = bval; }
 }
 
-// ---- vnorm: normalise the stored row residual (hodlr.h:194), partial ||v||^2 and V_prev^T v -----------------------
-__device__ __forceinline__ void a2_vnorm_body(const A2Args& a, int chunk, double* s_v, double* red) {
+// ---- vnorm: normalise the stored row residual (hodlr.h:194), partial ||v||^2 and V_prev^T v, group maxima ------------
+__device__ __forceinline__ void a2_vnorm_body(const A2Args& a, int chunk, int sub, double* s_v, double* red) {
   const int nid = a.cchunk_node[chunk];
   const A2State& st = a.states[nid];
   if (st.phase != A2_ACCEPT || !st.active) return;
   const A2Node nd = a.nodes[nid];
   const int rank = st.rank;
   const int lc = chunk - nd.cchunk0;
-  const int c_lo = lc * A2_CHUNK;
-  const int c_n = min(A2_CHUNK, nd.n_cols - c_lo);
+  const int c_lo = lc * A2_CHUNK + sub * A2_THREADS;
+  if (c_lo >= nd.n_cols) return;
+  const int c_n = min(A2_THREADS, nd.n_cols - c_lo);
   double* Vcols = a.Vp + (int64_t)nd.vcol * a.ld;
   const double pivot = st.pivot;
-  double vn2 = 0.0;
-#pragma unroll
-  for (int e = 0; e < A2_EPT; ++e) {
-    const int n = threadIdx.x + e * A2_THREADS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double vn2 = 0.0, av = 0.0;
+  {
+    const int n = threadIdx.x;
+    double v = 0.0;
     if (n < c_n) {
       double* pv = Vcols + (int64_t)rank * a.ld + nd.col0 + c_lo + n;
-      const double v = *pv / pivot;
+      v = *pv / pivot;
       *pv = v;
-      s_v[n] = v;
-      vn2 += v * v;
+      vn2 = v * v;
+      av = fabs(v);
+      if (v != v) av = __longlong_as_double(0x7ff0000000000000ll);
     }
+    s_v[n] = v;
   }
-  vn2 = block_sum(vn2, red);
-  double* part = a.vpart + (int64_t)chunk * (a.capmax + 1);
+  if (a.vmax) {  // max |v| of the two 128-column groups of this sub-chunk (warps 0-3 | 4-7)
+    av = warp_max(av);
+    if (lane == 0) red[16 + warp] = av;
+  }
+  vn2 = block_sum(vn2, red);  // (two barriers: s_v and red[16..] visible)
+  if (a.vmax && threadIdx.x < 2) {
+    const int g = threadIdx.x;
+    const double m = fmax(fmax(red[16 + 4 * g], red[17 + 4 * g]), fmax(red[18 + 4 * g], red[19 + 4 * g]));
+    a.vmax[((int64_t)chunk * A2_NGROUP + sub * 2 + g) * a.capmax + rank] = m;
+  }
+  double* part = a.vpart + ((int64_t)chunk * A2_NSUB + sub) * (a.capmax + 1);
   if (threadIdx.x == 0) part[0] = vn2;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int k = warp; k < rank; k += A2_THREADS / 32) {
     const double* vk = Vcols + (int64_t)k * a.ld + nd.col0 + c_lo;
     double s = 0.0;
@@ -635,74 +726,63 @@ __device__ __forceinline__ void a2_vnorm_body(const A2Args& a, int chunk, double
 }
 
 // ---- ucol: column residual -> panel column `rank` (row part), partial ||u||^2 and U_prev^T u --------------------
-// vnorm (column chunks) and ucol (row chunks) are independent: one launch, blocks [0, n_cchunks) normalise, the rest
-// compute the column residual.
+// vnorm (column sub-chunks) and ucol (row sub-chunks) are independent: one launch, blocks [0, n_cchunks) normalise, the
+// rest compute the column residual.
+template <int SHAPE>
 __global__ void __launch_bounds__(A2_THREADS) a2_vnorm_ucol_kernel(A2Args a, int n_cchunks_total) {
   __shared__ DevProgram P;
   __shared__ double s_x[ACA_MAX_NDIM];
   __shared__ double s_vr[128];
-  __shared__ double s_u[A2_CHUNK];
+  __shared__ double s_u[A2_THREADS];
   __shared__ double red[32];
-  if ((int)blockIdx.x < n_cchunks_total) { a2_vnorm_body(a, blockIdx.x, s_u, red); return; }
+  const int sub = blockIdx.y;
+  if ((int)blockIdx.x < n_cchunks_total) { a2_vnorm_body(a, blockIdx.x, sub, s_u, red); return; }
   const int chunk = blockIdx.x - n_cchunks_total;
   const int nid = a.rchunk_node[chunk];
   const A2State& st = a.states[nid];
   if (st.phase != A2_ACCEPT || !st.active) return;
   const A2Node nd = a.nodes[nid];
-  stage_program(&P, a.prog);
+  const int lr = chunk - nd.rchunk0;
+  const int r_lo = lr * A2_CHUNK + sub * A2_THREADS;
+  if (r_lo >= nd.n_rows) return;
+  if constexpr (SHAPE == BGP_SHAPE_GENERIC) stage_program(&P, a.prog);
   const int ndim = a.prog->ndim;
   const int rank = st.rank;
-  const int lr = chunk - nd.rchunk0;
-  const int r_lo = lr * A2_CHUNK;
-  const int r_n = min(A2_CHUNK, nd.n_rows - r_lo);
+  const int r_n = min(A2_THREADS, nd.n_rows - r_lo);
   double* Vcols = a.Vp + (int64_t)nd.vcol * a.ld;
-  const double* xr = a.x + (int64_t)(nd.row0 + r_lo) * ndim;
   const int j = st.piv_j;
   for (int q = threadIdx.x; q < ndim; q += A2_THREADS) s_x[q] = a.x[(int64_t)(nd.col0 + j) * ndim + q];
   __syncthreads();
-  double vals[A2_EPT];
-#pragma unroll
-  for (int e = 0; e < A2_EPT; ++e) {
-    const int n = threadIdx.x + e * A2_THREADS;
-    vals[e] = (n < r_n) ? kernel_value(P, xr + (int64_t)n * ndim, s_x) : 0.0;
-  }
-  for (int k0 = 0; k0 < rank; k0 += 128) {
-    const int nk = min(128, rank - k0);
-    __syncthreads();
-    // V(j, k) for k < rank: columns already normalised in earlier iterations
-    for (int k = threadIdx.x; k < nk; k += A2_THREADS) s_vr[k] = __ldcg(Vcols + (int64_t)(k0 + k) * a.ld + nd.col0 + j);
-    __syncthreads();
-#pragma unroll 4
-    for (int k = 0; k < nk; ++k) {
-      const double v = s_vr[k];
-#pragma unroll
-      for (int e = 0; e < A2_EPT; ++e) {
-        const int n = threadIdx.x + e * A2_THREADS;
-        if (n < r_n) vals[e] -= v * Vcols[(int64_t)(k0 + k) * a.ld + nd.row0 + r_lo + n];
-      }
-    }
-  }
+  const auto fn = ShapeEval<SHAPE>::make(&P, a.prog);
+  const int n = threadIdx.x;
+  const bool act = n < r_n;
+  const int nn = act ? n : 0;
+  // V(j, q) for q < rank: columns already normalised in earlier iterations
+  const double val = a2_resid_entry(fn, a.x + (int64_t)(nd.row0 + r_lo + nn) * ndim, s_x, rank, Vcols + nd.row0 + r_lo + nn, a.ld,
+                                    Vcols + nd.col0 + j, s_vr, act);
   double un2 = 0.0;
-#pragma unroll
-  for (int e = 0; e < A2_EPT; ++e) {
-    const int n = threadIdx.x + e * A2_THREADS;
-    if (n < r_n) {
-      Vcols[(int64_t)rank * a.ld + nd.row0 + r_lo + n] = vals[e];
-      s_u[n] = vals[e];
-      un2 += vals[e] * vals[e];
-    }
+  if (act) {
+    Vcols[(int64_t)rank * a.ld + nd.row0 + r_lo + n] = val;
+    un2 = val * val;
   }
+  s_u[n] = act ? val : 0.0;
   un2 = block_sum(un2, red);
-  double* part = a.upart + (int64_t)chunk * (a.capmax + 1);
+  double* part = a.upart + ((int64_t)chunk * A2_NSUB + sub) * (a.capmax + 1);
   if (threadIdx.x == 0) part[0] = un2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int k = warp; k < rank; k += A2_THREADS / 32) {
     const double* uk = Vcols + (int64_t)k * a.ld + nd.row0 + r_lo;
     double s = 0.0;
-    for (int n = lane; n < r_n; n += 32) s += uk[n] * s_u[n];
+    for (int n2 = lane; n2 < r_n; n2 += 32) s += uk[n2] * s_u[n2];
     s = warp_sum(s);
     if (lane == 0) part[1 + k] = s;
   }
+}
+inline void a2_vrow_launch(int shape, dim3 grid, cudaStream_t s, const A2Args& a) {
+  BGP_SHAPE_SWITCH(shape, (a2_vrow_kernel<SHAPE><<<grid, A2_THREADS, 0, s>>>(a)));
+}
+inline void a2_vnorm_ucol_launch(int shape, dim3 grid, cudaStream_t s, const A2Args& a, int ncc) {
+  BGP_SHAPE_SWITCH(shape, (a2_vnorm_ucol_kernel<SHAPE><<<grid, A2_THREADS, 0, s>>>(a, ncc)));
 }
 
 // ---- finish: stopping rule (hodlr.h:202-214), next candidates -----------------------------------------------------
@@ -716,15 +796,19 @@ __global__ void __launch_bounds__(A2_THREADS) a2_finish_kernel(A2Args a) {
   const A2Node nd = a.nodes[nid];
   const int rank = st.rank;
   double vn2 = 0.0, un2 = 0.0;
-  for (int c = threadIdx.x; c < nd.n_cchunks; c += blockDim.x) vn2 += a.vpart[(int64_t)(nd.cchunk0 + c) * (a.capmax + 1)];
-  for (int c = threadIdx.x; c < nd.n_rchunks; c += blockDim.x) un2 += a.upart[(int64_t)(nd.rchunk0 + c) * (a.capmax + 1)];
+  // sub-chunk slots of a node are contiguous: slot = chunk * A2_NSUB + sub; the ones past the node's end were never written
+  const int nvs = (nd.n_cols + A2_THREADS - 1) / A2_THREADS, nus = (nd.n_rows + A2_THREADS - 1) / A2_THREADS;
+  const double* vp0 = a.vpart + (int64_t)nd.cchunk0 * A2_NSUB * (a.capmax + 1);
+  const double* up0 = a.upart + (int64_t)nd.rchunk0 * A2_NSUB * (a.capmax + 1);
+  for (int c = threadIdx.x; c < nvs; c += blockDim.x) vn2 += vp0[(int64_t)c * (a.capmax + 1)];
+  for (int c = threadIdx.x; c < nus; c += blockDim.x) un2 += up0[(int64_t)c * (a.capmax + 1)];
   vn2 = block_sum(vn2, S.red);
   un2 = block_sum(un2, S.red);
   double vdot = 0.0, udot = 0.0;
   for (int k = threadIdx.x; k < rank; k += blockDim.x) {
     double sv = 0.0, su = 0.0;
-    for (int c = 0; c < nd.n_cchunks; ++c) sv += a.vpart[(int64_t)(nd.cchunk0 + c) * (a.capmax + 1) + 1 + k];
-    for (int c = 0; c < nd.n_rchunks; ++c) su += a.upart[(int64_t)(nd.rchunk0 + c) * (a.capmax + 1) + 1 + k];
+    for (int c = 0; c < nvs; ++c) sv += vp0[(int64_t)c * (a.capmax + 1) + 1 + k];
+    for (int c = 0; c < nus; ++c) su += up0[(int64_t)c * (a.capmax + 1) + 1 + k];
     vdot = fmax(vdot, fabs(sv));
     udot = fmax(udot, fabs(su));
   }

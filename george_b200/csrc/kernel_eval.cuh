@@ -27,9 +27,11 @@ struct DevLeaf {
 struct DevProgram {
   int n_nodes, ndim, n_params_total, n_leaves;
   int flags;  // bit0: 1-D input and every leaf depends on d = x1 - x2 only (fast path)
-  int shape;  // 0 generic; otherwise BGP_SHAPE_*: the whole program is  sc * f(d*d*sm)  with f a stationary profile
+  int shape;  // 0 generic; otherwise BGP_SHAPE_*: the whole program is  sc * f(d*d*sm)  with f a stationary profile,
+              // or one of the two-term 1-D forms  sc*f(d*d*sm) + sc2*ExpSine2  /  (sc*f(d*d*sm)) * ExpSine2
   int _pad[2];
   double sc, sm;
+  double sc2, sg, sw;  // two-term shapes: scale of the periodic term, its Gamma and pi / period (kernels.h:1513-1537)
   signed char code[BGP_MAX_NODES];  // >=0: leaf index, -1: sum, -2: product
   DevLeaf leaf[BGP_MAX_LEAVES];
 };
@@ -217,28 +219,65 @@ __device__ __forceinline__ double leaf_value(const DevLeaf& L, const double* x1,
 // Fast path for 1-D inputs whose leaves all depend on d = x1 - x2 only (stationary kernels with a scalar metric,
 // ExpSine2, Cosine, Constant): no axis indirection, no metric loops.  Same arithmetic, same order, as the general path.
 #define BGP_FLAG_FAST1D 1
-enum { BGP_SHAPE_GENERIC = 0, BGP_SHAPE_EXPSQ = 1, BGP_SHAPE_M32 = 2, BGP_SHAPE_M52 = 3, BGP_SHAPE_EXP = 4 };
+enum {
+  BGP_SHAPE_GENERIC = 0, BGP_SHAPE_EXPSQ = 1, BGP_SHAPE_M32 = 2, BGP_SHAPE_M52 = 3, BGP_SHAPE_EXP = 4,
+  // two-term programs on 1-D inputs (the usual quasi-periodic models):  c*A + c2*ExpSine2  and  (c*A) * ExpSine2
+  BGP_SHAPE_SUM_EXPSQ_ES2 = 5, BGP_SHAPE_SUM_M32_ES2 = 6, BGP_SHAPE_PROD_EXPSQ_ES2 = 7, BGP_SHAPE_PROD_M32_ES2 = 8,
+  BGP_NUM_SHAPES = 9
+};
+__host__ __device__ constexpr int shape_profile(int shape) {  // the stationary profile a shape is built on
+  return shape <= BGP_SHAPE_EXP ? shape
+         : (shape == BGP_SHAPE_SUM_EXPSQ_ES2 || shape == BGP_SHAPE_PROD_EXPSQ_ES2) ? (int)BGP_SHAPE_EXPSQ : (int)BGP_SHAPE_M32;
+}
+__host__ __device__ constexpr bool shape_is_sum(int shape) { return shape == BGP_SHAPE_SUM_EXPSQ_ES2 || shape == BGP_SHAPE_SUM_M32_ES2; }
+__host__ __device__ constexpr bool shape_is_prod(int shape) { return shape == BGP_SHAPE_PROD_EXPSQ_ES2 || shape == BGP_SHAPE_PROD_M32_ES2; }
+// |k| has a usable decreasing bound in the distance (everything but the sums with a periodic term, which never decay)
+__host__ __device__ constexpr bool shape_has_bound(int shape) { return shape != BGP_SHAPE_GENERIC && !shape_is_sum(shape); }
 
-// compile-time specialised evaluators for the commonest programs ("c * StationaryKernel(metric)" on 1-D inputs):
-// the interpreter disappears and independent evaluations can be interleaved by the compiler.
+// radial profile f(r2) of the specialised evaluators.  exp(-t) rounds to exactly 0 in double for t > 745.14: far-apart
+// pairs (the bulk of every large off-diagonal block) skip the software exp/sqrt; the branch is warp-uniform because a
+// warp sweeps 32 neighbouring points.  Same expressions, same order, as leaf_value_1d / radial_value.
+template <int PROFILE>
+__device__ __forceinline__ double profile_value(double r2) {
+  if (PROFILE == BGP_SHAPE_EXPSQ) return (r2 > 1490.4) ? 0.0 : exp(-0.5 * r2);
+  if (PROFILE == BGP_SHAPE_M32) {
+    if (r2 > 185200.0) return 0.0;  // sqrt(3 r2) > 745.3
+    const double r = sqrt(3.0 * r2);
+    return (1.0 + r) * exp(-r);
+  }
+  if (PROFILE == BGP_SHAPE_M52) {
+    if (r2 > 111100.0) return 0.0;  // sqrt(5 r2) > 745.3
+    const double r = sqrt(5.0 * r2);
+    return (1 + r + 5.0 * r2 / 3.0) * exp(-r);
+  }
+  return (r2 > 555400.0) ? 0.0 : exp(-sqrt(r2));  // sqrt(r2) > 745.2
+}
+
+// compile-time specialised evaluators for the commonest programs on 1-D inputs: the interpreter disappears and
+// independent evaluations can be interleaved by the compiler.  The operators of the two-term shapes are spelled with
+// round-to-nearest intrinsics so that no multiply-add contraction can make them differ from the interpreter, which
+// applies Sum / Product (kernels.h:78-80, 114-116) one node at a time.
 template <int SHAPE>
 struct ScaledProfile1D {
-  double c, m;
+  double c, m, c2, g, w;
+  __device__ __forceinline__ explicit ScaledProfile1D(const DevProgram& P) : c(P.sc), m(P.sm), c2(P.sc2), g(P.sg), w(P.sw) {}
+  __device__ __forceinline__ ScaledProfile1D(double c_, double m_) : c(c_), m(m_), c2(0.0), g(0.0), w(0.0) {}
   __device__ __forceinline__ double operator()(const double* x1, const double* x2) const {
     const double d = x1[0] - x2[0];
     const double r2 = d * d * m;
-    double f;
-    // exp(-t) rounds to exactly 0 in double for t > 745.14: far-apart pairs (the bulk of every large off-diagonal
-    // block) skip the software exp/sqrt; the branch is warp-uniform because a warp sweeps 32 neighbouring points.
-    if (SHAPE == BGP_SHAPE_EXPSQ) f = (r2 > 1490.4) ? 0.0 : exp(-0.5 * r2);
-    else if (SHAPE == BGP_SHAPE_M32) {
-      if (r2 > 185200.0) f = 0.0;  // sqrt(3 r2) > 745.3
-      else { const double r = sqrt(3.0 * r2); f = (1.0 + r) * exp(-r); }
-    } else if (SHAPE == BGP_SHAPE_M52) {
-      if (r2 > 111100.0) f = 0.0;  // sqrt(5 r2) > 745.3
-      else { const double r = sqrt(5.0 * r2); f = (1 + r + 5.0 * r2 / 3.0) * exp(-r); }
-    } else f = (r2 > 555400.0) ? 0.0 : exp(-sqrt(r2));  // sqrt(r2) > 745.2
-    return c * f;
+    const double a = __dmul_rn(c, profile_value<shape_profile(SHAPE)>(r2));
+    if (SHAPE <= BGP_SHAPE_EXP) return a;
+    const double s = sin(d * w);
+    const double e = exp(-g * s * s);
+    if (shape_is_sum(SHAPE)) return __dadd_rn(a, __dmul_rn(c2, e));
+    return __dmul_rn(a, e);
+  }
+  // upper bound of |k(x1, x2)| over all pairs at distance >= gap (monotone profiles; the periodic factor is <= 1).
+  // Only meaningful when shape_has_bound(SHAPE).
+  __device__ __forceinline__ double bound(double gap) const {
+    double b = fabs(c) * profile_value<shape_profile(SHAPE)>(gap * gap * m);
+    if (shape_is_prod(SHAPE) && g < 0.0) b *= exp(-g);  // exp(-Gamma sin^2) <= 1 only for Gamma >= 0
+    return b;
   }
 };
 __device__ __forceinline__ double leaf_value_1d(const DevLeaf& L, double d) {
@@ -302,6 +341,31 @@ struct GenericKernelFn {
     case BGP_SHAPE_EXP: { ScaledProfile1D<BGP_SHAPE_EXP> fn{(P).sc, (P).sm}; BODY; } break;           \
     default: { GenericKernelFn fn{&(P)}; BODY; } break;                                               \
   }
+// host side: call FN<SHAPE>(args...) for the runtime shape (every shape, incl. the two-term ones)
+#define BGP_SHAPE_SWITCH(shape, CALL)                                                                 \
+  switch (shape) {                                                                                    \
+    case BGP_SHAPE_EXPSQ: { constexpr int SHAPE = BGP_SHAPE_EXPSQ; CALL; } break;                     \
+    case BGP_SHAPE_M32: { constexpr int SHAPE = BGP_SHAPE_M32; CALL; } break;                         \
+    case BGP_SHAPE_M52: { constexpr int SHAPE = BGP_SHAPE_M52; CALL; } break;                         \
+    case BGP_SHAPE_EXP: { constexpr int SHAPE = BGP_SHAPE_EXP; CALL; } break;                         \
+    case BGP_SHAPE_SUM_EXPSQ_ES2: { constexpr int SHAPE = BGP_SHAPE_SUM_EXPSQ_ES2; CALL; } break;     \
+    case BGP_SHAPE_SUM_M32_ES2: { constexpr int SHAPE = BGP_SHAPE_SUM_M32_ES2; CALL; } break;         \
+    case BGP_SHAPE_PROD_EXPSQ_ES2: { constexpr int SHAPE = BGP_SHAPE_PROD_EXPSQ_ES2; CALL; } break;   \
+    case BGP_SHAPE_PROD_M32_ES2: { constexpr int SHAPE = BGP_SHAPE_PROD_M32_ES2; CALL; } break;       \
+    default: { constexpr int SHAPE = BGP_SHAPE_GENERIC; CALL; } break;                                \
+  }
+
+// evaluator object of a shape, built inside a kernel: the interpreter needs the staged program, the rest only scalars
+template <int SHAPE>
+struct ShapeEval {
+  using type = ScaledProfile1D<SHAPE>;
+  static __device__ __forceinline__ type make(const DevProgram* /*staged*/, const DevProgram* g) { return type(*g); }
+};
+template <>
+struct ShapeEval<BGP_SHAPE_GENERIC> {
+  using type = GenericKernelFn;
+  static __device__ __forceinline__ type make(const DevProgram* staged, const DevProgram* /*g*/) { return type{staged}; }
+};
 
 // value + hyper-parameter gradient (kernels.h:81-94 Sum, 117-139 Product, per-leaf gradient() methods).
 // grad has n_params_total entries; entries with which[i]==0 are 0.  Not on the log-likelihood hot path.

@@ -121,9 +121,11 @@ class HODLRSolver(object):
         _lib.check(self._lib.bgp_hodlr_set_profiling(self._ptr, 1 if on else 0))
 
     def aca_profile(self):
-        p = (C.c_double * 5)()
+        p = (C.c_double * 12)()
         _lib.check(self._lib.bgp_hodlr_last_aca_profile(self._ptr, p))
-        return dict(zip(("eval_ms", "eval_launches", "evals", "update_fmas", "candidates"), list(p)))
+        out = dict(zip(("eval_ms", "eval_launches", "evals", "update_fmas", "candidates", "evaluated"), list(p)[:6]))
+        out["kernel_ms"] = dict(zip(("a2_eval", "a2_decide", "a2_vrow", "a2_pivot", "a2_vnorm_ucol", "a2_finish"), list(p)[6:]))
+        return out
 
     def work(self):
         w = (C.c_double * 6)()

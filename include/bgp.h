@@ -261,17 +261,22 @@ int bgp_hodlr_num_nodes(const bgp_hodlr_t* h, int64_t* out);
 int bgp_hodlr_node_info(const bgp_hodlr_t* h, bgp_hodlr_node_info_t* out /* num_nodes */);
 /* ACA pivots of node `node` (pre-order index): rows[k], cols[k] for k < rank, block-relative. */
 int bgp_hodlr_node_pivots(const bgp_hodlr_t* h, int64_t node, int32_t* rows, int32_t* cols);
-/* Device-event timings of the last compute, ms: [0] leaves (build+factor), [1] ACA, [2] up-sweep,
- * [3] total compute, [4] last solve. */
+/* Device-event timings of the last compute, ms: [0] leaves (build+factor; stream A, CONCURRENT with [1]),
+ * [1] ACA (stream B, from the start of compute), [2] up-sweep (panel finalisation + leaf solves + level sweeps, from the
+ * moment both streams have drained), [3] total compute, [4] last solve.  [3] ~ max([0], [1]) + host gap + [2]. */
 int bgp_hodlr_last_timing(const bgp_hodlr_t* h, double* ms5);
 /* Algorithmic work of the last compute: [0] kernel evaluations, [1] bytes, [2] flops,
  * [3] sum of per-level max ranks R, [4] leaf size m, [5] number of levels. */
 int bgp_hodlr_last_work(const bgp_hodlr_t* h, double* w6);
-/* Optional per-kernel timing of the ACA's dominant kernel (a2_eval_kernel): with profiling on, every launch is
- * bracketed by CUDA events on its stream.  p5 = [0] summed launch time ms, [1] launches (= lock-step iterations),
- * [2] candidate-row kernel evaluations, [3] residual-update FMAs, [4] candidate rows examined. */
+/* Optional per-kernel timing of the lock-step ACA loop: with profiling on, every launch is bracketed by CUDA events on
+ * its stream.  p12 = [0] summed a2_eval launch time ms, [1] launches of each kernel (= lock-step iterations),
+ * [2] candidate-row entries verified against the 1e-14 pivot threshold (hodlr.h:191), [3] residual-update FMAs,
+ * [4] candidate rows examined, [5] entries of [2] that were actually evaluated (the others were bounded below the
+ * threshold from the kernel's decay and the factor magnitudes, without evaluation; decisions are identical),
+ * [6..11] summed launch times ms of a2_eval (+ its all-reduce when sharded), a2_decide, a2_vrow, a2_pivot,
+ * a2_vnorm_ucol, a2_finish. */
 int bgp_hodlr_set_profiling(bgp_hodlr_t* h, int on);
-int bgp_hodlr_last_aca_profile(const bgp_hodlr_t* h, double* p5);
+int bgp_hodlr_last_aca_profile(const bgp_hodlr_t* h, double* p12);
 
 /* Diagnostics: the dense building blocks of the big-rank Woodbury step (csrc/hodlr_lu.cuh, csrc/gemm_dmma.cuh),
  * callable on their own with HOST pointers so the tests can check them against LAPACK.

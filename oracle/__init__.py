@@ -49,6 +49,8 @@ def lib():
             getattr(L, name).argtypes = args
         L.oracle_hodlr_compute.restype = vp
         L.oracle_hodlr_compute.argtypes = [vp, vp, i64, i32, vp, i32, dbl, i32, i32]
+        L.oracle_hodlr_compute2.restype = vp
+        L.oracle_hodlr_compute2.argtypes = [vp, vp, i64, i32, vp, i32, dbl, i32, i32, i32]
         L.oracle_hodlr_free.restype = None
         L.oracle_hodlr_free.argtypes = [vp]
         L.oracle_hodlr_log_determinant.restype = dbl
@@ -128,14 +130,17 @@ NODE_FIELDS = ("start", "size", "half", "is_leaf", "parent", "direction", "depth
 class HODLR(object):
     """The restated reference solver (``_hodlr.cpp:36-112``)."""
 
-    def __init__(self, spec, x, yerr, min_size=100, tol=0.1, seed=42, rng_mode=1):
+    def __init__(self, spec, x, yerr, min_size=100, tol=0.1, seed=42, rng_mode=1, exhaust=0):
+        """rng_mode: 1 = the reference's single shared mt19937 (hodlr.h:35,58-61), 0 = one stream per node (the CUDA
+        path's level-parallel mode).  exhaust: 0 = the reference's dense fallback (hodlr.h:161-176), 1 = keep the
+        low-rank factors when every row has been rejected (the CUDA path's ``exhaust="lowrank"``)."""
         x = _c(x)
         if x.ndim == 1:
             x = x[:, None]
         yerr = _c(yerr)
         self.n = len(x)
-        self._h = lib().oracle_hodlr_compute(C.byref(spec), _p(x), len(x), x.shape[1], _p(yerr), int(min_size),
-                                             float(tol), int(seed), int(rng_mode))
+        self._h = lib().oracle_hodlr_compute2(C.byref(spec), _p(x), len(x), x.shape[1], _p(yerr), int(min_size),
+                                              float(tol), int(seed), int(rng_mode), int(exhaust))
         if not self._h:
             raise ValueError("oracle: invalid kernel program")
 

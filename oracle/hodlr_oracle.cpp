@@ -163,6 +163,8 @@ struct Node {
 struct Solver {
   Program prog;
   int n = 0, ndim = 0, min_size = 100, rng_mode = BGP_RNG_REFERENCE;
+  int exhaust_mode = BGP_EXHAUST_DENSE;  // BGP_EXHAUST_LOWRANK: the documented deviation of the CUDA path, restated
+                                         // here so that the two can be compared one to one in that mode as well
   uint32_t seed = 42;
   double tol = 0.1;
   std::vector<double> x, diag;
@@ -197,6 +199,13 @@ static int low_rank_approx(Solver* S, Node* nd, int start_row, int n_rows, int s
     do {
       if (index.empty()) {  // hodlr.h:161-176 dense fallback
         nd->dense_fallback = 1;
+        if (S->exhaust_mode == BGP_EXHAUST_LOWRANK) {
+          // NOT the reference: every row has been tried and none has a residual entry >= 1e-14, so the factors found
+          // so far reproduce the block to 1e-14 per entry; keep them instead of storing the block densely.
+          U_out = Mat(n_rows, rank); V_out = Mat(n_cols, rank);
+          for (int q = 0; q < rank; ++q) { std::memcpy(U_out.col(q), U[q].data(), sizeof(double) * n_rows); std::memcpy(V_out.col(q), V[q].data(), sizeof(double) * n_cols); }
+          return rank;
+        }
         U_out = Mat(n_rows, max_rank); V_out = Mat(n_cols, max_rank);
         if (n_cols <= n_rows) {
           for (int m = 0; m < n_cols; ++m) { V_out(m, m) = 1.0; for (int n = 0; n < n_rows; ++n) U_out(n, m) = S->K(start_row + n, start_col + m); }
@@ -415,11 +424,12 @@ int oracle_x_gradient_general(const bgp_kernel_spec_t* spec, int side, const dou
 }
 
 // _hodlr.cpp:55-94
-void* oracle_hodlr_compute(const bgp_kernel_spec_t* spec, const double* x, int64_t n, int32_t ndim, const double* yerr,
-                           int32_t min_size, double tol, int32_t seed, int32_t rng_mode) {
+void* oracle_hodlr_compute2(const bgp_kernel_spec_t* spec, const double* x, int64_t n, int32_t ndim, const double* yerr,
+                            int32_t min_size, double tol, int32_t seed, int32_t rng_mode, int32_t exhaust_mode) {
   Solver* S = new Solver();
   if (build_program(spec, &S->prog) || S->prog.ndim != ndim) { delete S; return nullptr; }
   S->n = (int)n; S->ndim = ndim; S->min_size = min_size; S->tol = tol; S->seed = (uint32_t)seed; S->rng_mode = rng_mode;
+  S->exhaust_mode = exhaust_mode;
   S->x.assign(x, x + (size_t)n * ndim);
   S->diag.resize(n);
   for (int64_t i = 0; i < n; ++i) S->diag[i] = yerr[i] * yerr[i];
@@ -429,6 +439,10 @@ void* oracle_hodlr_compute(const bgp_kernel_spec_t* spec, const double* x, int64
   compute(S->root.get());
   S->log_det = S->root->log_det;
   return S;
+}
+void* oracle_hodlr_compute(const bgp_kernel_spec_t* spec, const double* x, int64_t n, int32_t ndim, const double* yerr,
+                           int32_t min_size, double tol, int32_t seed, int32_t rng_mode) {
+  return oracle_hodlr_compute2(spec, x, n, ndim, yerr, min_size, tol, seed, rng_mode, BGP_EXHAUST_DENSE);
 }
 void oracle_hodlr_free(void* h) { delete (Solver*)h; }
 double oracle_hodlr_log_determinant(void* h) { return ((Solver*)h)->log_det; }

@@ -201,3 +201,89 @@ def test_exhaust_lowrank_matches_dense_mode(gpu, oracle):
     assert max(nd["rank"] for nd in res["lowrank"][2]) <= 3
     assert any(nd["dense_fallback"] for nd in res["lowrank"][2])   # the flag still reports the exhausted nodes
     assert max(nd["rank"] for nd in res["dense"][2]) >= 100         # reference semantics: rank = min(rows, cols)
+
+
+def _pivot_lists(s, nodes):
+    out = []
+    for i, nd in enumerate(nodes):
+        if nd["is_leaf"]:
+            out.append(None)
+        else:
+            r, c = s.pivots(i, nd["rank"])
+            out.append((list(r), list(c)))
+    return out
+
+
+@pytest.mark.parametrize("kname,n,min_size", [("m32", 6000, 100), ("m32", 20000, 256), ("expsq", 20000, 100),
+                                               ("m52", 9000, 100), ("exp", 5000, 64), ("prod_expsq_es2", 12000, 100)])
+def test_bound_culling_is_decision_exact(gpu, monkeypatch, kname, n, min_size):
+    """a2_eval skips (candidate row, 128-column group) pairs whose residual is PROVABLY < 1e-14 (kernel bound at the gap
+    + |U| * max|V|).  That must not change a single decision: ranks, RNG draws, exhausted flags and pivot lists are
+    identical to the exhaustive scan (BGP_NO_CULL=1), and so are the scalars, bit for bit."""
+    from george_b200 import kernels as K
+    from george_b200.solvers._hodlr import HODLRSolver
+    rng = np.random.default_rng(21)
+    x = np.sort(rng.uniform(0, 10 * n / 1000, n))[:, None]
+    yerr = 0.1 * np.ones(n)
+    y = np.sin(x[:, 0]) + 0.1 * rng.normal(size=n)
+    kernel = {"m32": 1.0 * K.Matern32Kernel(1.0), "expsq": 1.5 * K.ExpSquaredKernel(2.0), "m52": K.Matern52Kernel(0.7),
+              "exp": 0.8 * K.ExpKernel(1.0),
+              "prod_expsq_es2": 1.2 * K.ExpSquaredKernel(50.0) * K.ExpSine2Kernel(gamma=1.0, log_period=np.log(3.0))}[kname]
+    res = {}
+    for cull in (True, False):
+        if cull:
+            monkeypatch.delenv("BGP_NO_CULL", raising=False)
+        else:
+            monkeypatch.setenv("BGP_NO_CULL", "1")
+        s = HODLRSolver()
+        s.compute(kernel, x, yerr, min_size=min_size, tol=1e-10, seed=42, exhaust="lowrank")
+        nodes = s.nodes()
+        prof = s.aca_profile()
+        res[cull] = (s.log_determinant, s.dot_solve(y), [(nd["rank"], nd["rng_draws"], nd["dense_fallback"]) for nd in nodes],
+                     _pivot_lists(s, nodes), prof)
+    monkeypatch.delenv("BGP_NO_CULL", raising=False)
+    assert res[True][2] == res[False][2]
+    assert res[True][3] == res[False][3]
+    assert res[True][0] == res[False][0] and res[True][1] == res[False][1]
+    # the culled run verified the same number of entries and evaluated no more than the exhaustive one
+    assert res[True][4]["evals"] == res[False][4]["evals"]
+    assert res[True][4]["evaluated"] <= res[False][4]["evaluated"]
+    assert res[False][4]["evaluated"] == res[False][4]["evals"]
+
+
+@pytest.mark.parametrize("kname", ["expsq", "sum_expsq_es2", "prod_expsq_es2", "sum_m32_es2", "prod_m32_es2", "m32"])
+def test_lowrank_mode_matches_oracle_lowrank(gpu, oracle, kname):
+    """exhaust='lowrank' + per-node RNG streams, the mode the headline runs in, against the oracle restated in the SAME
+    mode (oracle.HODLR(rng_mode=0, exhaust=1)): structure, ranks, draws, pivots and scalars.  The specialised two-term
+    evaluators (c*A + c2*ExpSine2, (c*A)*ExpSine2) are exercised here too: they must take the interpreter's decisions."""
+    from george_b200 import kernels as K
+    from george_b200.solvers._hodlr import HODLRSolver
+    from george_b200._spec import flatten
+    rng = np.random.default_rng(33)
+    n = 2500
+    x = np.sort(rng.uniform(0, 10 * n / 1000, n))[:, None]
+    yerr = 0.1 * np.ones(n)
+    y = np.sin(x[:, 0]) + 0.1 * rng.normal(size=n)
+    es2 = K.ExpSine2Kernel(gamma=1.0, log_period=np.log(3.0))
+    kernel = {"expsq": 1.0 * K.ExpSquaredKernel(1.0), "m32": 1.0 * K.Matern32Kernel(1.0),
+              "sum_expsq_es2": 1.0 * K.ExpSquaredKernel(1.0) + 0.5 * es2,
+              "prod_expsq_es2": 1.3 * K.ExpSquaredKernel(30.0) * es2,
+              "sum_m32_es2": 0.7 * K.Matern32Kernel(2.0) + es2,
+              "prod_m32_es2": K.Matern32Kernel(40.0) * es2}[kname]
+    s = HODLRSolver()
+    s.compute(kernel, x, yerr, min_size=100, tol=1e-10, seed=42, exhaust="lowrank")
+    o = oracle.HODLR(flatten(kernel), x, yerr, min_size=100, tol=1e-10, seed=42, rng_mode=0, exhaust=1)
+    gn, on = s.nodes(), o.nodes()
+    assert _structure(gn) == _structure(on)
+    assert abs(s.log_determinant - o.log_determinant) <= 1e-9 * abs(o.log_determinant)
+    assert abs(s.dot_solve(y) - o.dot_solve(y)) <= 1e-7 * abs(o.dot_solve(y))
+    if kname != "m32":  # m32: exactly rank 2, the third pivot is rounding noise of exp() (see test_values_vs_oracle_and_dense)
+        assert [(a["rank"], a["rng_draws"], a["dense_fallback"]) for a in gn] == \
+               [(b["rank"], b["rng_draws"], b["dense_fallback"]) for b in on]
+        for i, nd in enumerate(gn):
+            if not nd["is_leaf"]:
+                ra, ca = s.pivots(i, nd["rank"])
+                rb, cb = o.pivots(i, on[i]["rank"])
+                assert list(ra) == list(rb) and list(ca) == list(cb)
+    else:
+        assert max(nd["rank"] for nd in gn) <= 3
