@@ -86,7 +86,8 @@ struct bgp_hodlr {
   DevBuf<A2Node> d_a2nodes;
   DevBuf<A2State> d_a2states;
   DevBuf<A2EPart> d_epart;
-  DevBuf<int> d_cand, d_cand_k, d_cand_words, d_cchunk_node, d_rchunk_node, d_nactive;
+  DevBuf<int> d_cand, d_cand_k, d_cand_words, d_cand_L, d_cand_next, d_cand_live, d_cchunk_node, d_rchunk_node, d_nactive;
+  DevBuf<double> d_node_box;
   DevBuf<unsigned long long> d_cmax, d_stats;
   DevBuf<int4> d_work;
   DevBuf<int> d_work_count;
@@ -277,6 +278,10 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   BGP_TRY(h->d_cand.reserve((size_t)cand_total, s));
   BGP_TRY(h->d_cand_k.reserve((size_t)cand_total, s));
   BGP_TRY(h->d_cand_words.reserve((size_t)cand_total, s));
+  BGP_TRY(h->d_cand_L.reserve((size_t)cand_total, s));
+  BGP_TRY(h->d_cand_next.reserve((size_t)cand_total, s));
+  BGP_TRY(h->d_cand_live.reserve((size_t)cand_total, s));
+  BGP_TRY(h->d_node_box.reserve((size_t)2 * nn, s));
   BGP_TRY(h->d_cmax.reserve((size_t)cand_total, s));
   BGP_TRY(h->d_epart.reserve((size_t)std::max(ncc, 1) * A2_NSUB, s));
   BGP_TRY(h->d_cchunk_node.reserve(ncc, s));
@@ -306,6 +311,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   a.cand = h->d_cand.p; a.cand_k = h->d_cand_k.p; a.cand_words = h->d_cand_words.p; a.cmax = h->d_cmax.p; a.epart = h->d_epart.p;
   a.cchunk_node = h->d_cchunk_node.p; a.rchunk_node = h->d_rchunk_node.p; a.vpart = h->d_vpart.p; a.upart = h->d_upart.p;
   a.vmax = cull ? h->d_vmax.p : nullptr;
+  a.cand_L = h->d_cand_L.p; a.cand_next = h->d_cand_next.p; a.cand_live = h->d_cand_live.p; a.node_box = h->d_node_box.p;
   a.capmax = capmax; a.n_active = h->d_nactive.p; a.stats = h->d_stats.p;
   a.work = h->d_work.p; a.work_count = h->d_work_count.p; a.work_cap = (int)work_cap; a.iter = -1;
   a.shard_rank = dist_top ? h->opts.shard_rank : 0; a.shard_count = dist_top ? h->opts.shard_count : 1;
@@ -765,7 +771,7 @@ void bgp_hodlr_destroy(bgp_hodlr_t* h) {
   h->lu_ws.d_nodes.release(); h->lu_ws.d_trsm.release(); h->lu_ws.d_gemm.release(); h->d_gram_desc.release(); h->d_upd_desc.release();
   h->d_ticket.release(); h->d_chain_done.release(); h->d_ncols_by_depth.release(); h->d_chain_state.release();
   h->d_a2nodes.release(); h->d_a2states.release(); h->d_epart.release(); h->d_cand.release(); h->d_cand_k.release();
-  h->d_cand_words.release(); h->d_cchunk_node.release(); h->d_rchunk_node.release(); h->d_nactive.release();
+  h->d_cand_words.release(); h->d_cand_L.release(); h->d_cand_next.release(); h->d_cand_live.release(); h->d_node_box.release(); h->d_cchunk_node.release(); h->d_rchunk_node.release(); h->d_nactive.release();
   h->d_inv.release(); h->d_gscratch.release(); h->d_which.release();
   h->d_vpart.release(); h->d_upart.release(); h->d_vmax.release(); h->d_cmax.release(); h->d_stats.release(); h->d_work.release(); h->d_work_count.release();
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);

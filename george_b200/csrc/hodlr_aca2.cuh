@@ -116,154 +116,6 @@ __device__ inline void mt_skip_coop(MT19937& g, int n) {
   }
 }
 
-// shared-memory workspace of the per-node kernels (dynamic shared memory)
-struct A2NodeSmem {
-  MT19937 rng;
-  int k[A2_BMAX];       // drawn positions
-  int ok[A2_BMAX];      // index[k_c] before this batch
-  int ol[A2_BMAX];      // index[n_index-1-c] before this batch
-  int hkey[A2_HASH];    // overlay: position -> value after the swap-pops so far
-  int hval[A2_HASH];
-  uint32_t raw[A2_BMAX]; // raw mt19937 words of the batch
-  double red[32];
-  int redi[32];
-  int flag;
-};
-
-__device__ __forceinline__ int a2_hash_find(const int* hkey, int pos) {
-  unsigned h = ((unsigned)pos * 2654435761u) & (A2_HASH - 1);
-  while (hkey[h] != -1 && hkey[h] != pos) h = (h + 1) & (A2_HASH - 1);
-  return (int)h;
-}
-
-// Draw the next min(B, bmax, n_index) candidate rows speculatively: k_c = uniform(0, n_index-1-c) from `S.rng`
-// (advanced), swap-pop on the index list (hodlr.h:179-183).  The positions depend on the RNG only, so the list
-// entries they touch are prefetched by the whole CTA and the dependent swap-pop chain runs in shared memory.
-// cand[c] = row, cand_k[c] = position, words[c] = mt19937 words consumed up to and including draw c.
-__device__ inline void a2_generate(A2State& st, A2NodeSmem& S, int* __restrict__ index, int* __restrict__ cand,
-                                   int* __restrict__ cand_k, int* __restrict__ words, int bmax,
-                                   unsigned long long* __restrict__ cmax, const A2Node& nd, int nid, int4* work_next,
-                                   int* work_count_next, int work_cap, int shard_rank, int shard_count) {
-  const int n_index = st.n_index;
-  const int B = min(min(st.B, bmax), n_index);
-  // Lemire's multiply-shift rejects with probability s / 2^32 per draw; draw B words in parallel assuming none does and
-  // fall back to the one-word-at-a-time loop (from a saved state) in the rare batch where a rejection shows up.
-  if (threadIdx.x == 0) { S.flag = 0; st.ncand = B; }
-  const int idx0 = S.rng.idx;
-  mt_fill_coop(S.rng, S.raw, B);
-  for (int c = threadIdx.x; c < B; c += blockDim.x) {
-    const uint32_t srange = (uint32_t)(n_index - c);
-    const uint64_t prod = (uint64_t)S.raw[c] * (uint64_t)srange;
-    const uint32_t low = (uint32_t)prod;
-    if (low < srange && low < (0u - srange) % srange) S.flag = 1;
-    S.k[c] = (int)(prod >> 32);
-    words[c] = c + 1;
-    cmax[c] = 0ull;
-  }
-  for (int t = threadIdx.x; t < A2_HASH; t += blockDim.x) S.hkey[t] = -1;
-  __syncthreads();
-  if (S.flag) {
-    // exact replay: the batch consumed B words so far; rewind by re-deriving the state is not possible in place, so
-    // the caller-visible committed state (st.rng) is the restart point.
-    __syncthreads();
-    mt_copy(&S.rng, &st.rng);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int w = 0;
-      for (int c = 0; c < B; ++c) {
-        S.k[c] = mt_uniform(S.rng, (uint32_t)(n_index - c), &w);
-        words[c] = w;
-      }
-    }
-    __syncthreads();
-  }
-  (void)idx0;
-  for (int c = threadIdx.x; c < B; c += blockDim.x) {
-    S.ok[c] = index[S.k[c]];
-    S.ol[c] = index[n_index - 1 - c];
-  }
-  __syncthreads();
-  // Resolve the swap-pop chain.  Warp 0 takes the candidates 32 at a time: a group whose drawn positions are distinct and
-  // do not fall on the 32 "last" slots the group itself reads has no read-after-write dependence inside the group, so
-  // its look-ups and inserts run in parallel (writes of EARLIER groups are already in the overlay); the rare other
-  // groups are replayed one draw at a time by lane 0.  Same result as the sequential loop of hodlr.h:179-183.
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    for (int c0 = 0; c0 < B; c0 += 32) {
-      const int c = c0 + lane;
-      const bool valid = c < B;
-      const int pos = valid ? S.k[c] : (-2 - lane);
-      const int last = n_index - 1 - c;
-      const unsigned same = __match_any_sync(0xffffffffu, pos);
-      const bool dup = valid && (__popc(same) > 1);
-      const bool tail = valid && pos <= n_index - 1 - c0 && pos >= n_index - 1 - (c0 + 31);
-      const unsigned bad = __ballot_sync(0xffffffffu, dup || tail);
-      if (bad == 0u) {
-        int val = 0, lastval = 0;
-        if (valid) {
-          const int h = a2_hash_find(S.hkey, pos);
-          val = (S.hkey[h] == pos) ? S.hval[h] : S.ok[c];
-          const int hl = a2_hash_find(S.hkey, last);
-          lastval = (S.hkey[hl] == last) ? S.hval[hl] : S.ol[c];
-        }
-        __syncwarp();
-        if (valid) {
-          unsigned h = ((unsigned)pos * 2654435761u) & (A2_HASH - 1);
-          while (true) {
-            const int prev = atomicCAS(&S.hkey[h], -1, pos);
-            if (prev == -1 || prev == pos) break;
-            h = (h + 1) & (A2_HASH - 1);
-          }
-          S.hval[h] = lastval;
-          S.ok[c] = val;  // becomes cand[c]
-        }
-        __syncwarp();
-      } else {
-        if (lane == 0) {
-          const int cend = min(B, c0 + 32);
-          for (int cc = c0; cc < cend; ++cc) {
-            const int p2 = S.k[cc], l2 = n_index - 1 - cc;
-            const int h = a2_hash_find(S.hkey, p2);
-            const int val = (S.hkey[h] == p2) ? S.hval[h] : S.ok[cc];
-            S.ok[cc] = val;
-            const int hl = a2_hash_find(S.hkey, l2);
-            const int lastval = (S.hkey[hl] == l2) ? S.hval[hl] : S.ol[cc];
-            S.hkey[h] = p2;
-            S.hval[h] = lastval;
-          }
-        }
-        __syncwarp();
-      }
-    }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < B; c += blockDim.x) {
-    cand[c] = S.ok[c];
-    cand_k[c] = S.k[c];
-    const int h = a2_hash_find(S.hkey, S.k[c]);
-    index[S.k[c]] = S.hval[h];  // final content of every touched position (duplicates write the same value)
-  }
-  // publish the evaluation work of the NEXT eval launch: one item = (column chunk, A2_ITEM_CB candidate blocks).
-  // In a sharded run the chunks of a node above the cut are dealt round-robin to the ranks.
-  {
-    const int per_chunk = (B + A2_CG * A2_ITEM_CB - 1) / (A2_CG * A2_ITEM_CB);
-    int my_chunks = nd.n_cchunks;
-    const bool split = nd.is_top && shard_count > 1;
-    if (split) my_chunks = (nd.n_cchunks - shard_rank + shard_count - 1) / shard_count;
-    const int n_items = my_chunks * per_chunk;
-    if (threadIdx.x == 0) S.flag = atomicAdd(work_count_next, n_items);
-    __syncthreads();
-    const int base = S.flag;
-    for (int t = threadIdx.x; t < n_items; t += blockDim.x) {
-      const int ci = t / per_chunk, pi = t % per_chunk;
-      const int lc = split ? (shard_rank + ci * shard_count) : ci;
-      const int c0 = pi * A2_CG * A2_ITEM_CB;
-      if (base + t < work_cap) work_next[base + t] = make_int4(nd.cchunk0 + lc, c0, min(A2_CG * A2_ITEM_CB, B - c0), nid);
-    }
-  }
-  __syncthreads();
-}
-
 struct A2Args {
   const DevProgram* prog;
   const double* x;
@@ -281,6 +133,10 @@ struct A2Args {
   int* cand;       // candidate rows          [cand_off + c]
   int* cand_k;     // drawn positions
   int* cand_words; // cumulative words
+  int* cand_L;     // value the swap-pop of draw c writes to position cand_k[c] (the list entry that was last at that time)
+  int* cand_next;  // next draw of the batch that writes the same position (0x7fffffff: none): commit rule of a2_decide
+  int* cand_live;  // indices (into the batch) of the candidates that need evaluation, compacted; see a2_generate
+  double* node_box;  // [2 * node]: min / max coordinate of the node's columns (1-D bound culling)
   unsigned long long* cmax;  // per candidate: bit pattern of max |residual| over all chunks (atomicMax)
   A2EPart* epart;  // one slot per column sub-chunk: arg-max of the winning row's residual there
   const int* cchunk_node;  // chunk -> node
@@ -299,6 +155,176 @@ struct A2Args {
   unsigned long long* stats;  // [0] candidate-row entries verified (pairs), [1] residual-update FMAs executed, [2] candidates,
                               // [3] entries actually evaluated by a2_eval (the rest were bounded < 1e-14 without evaluation)
 };
+
+// shared-memory workspace of the per-node kernels (dynamic shared memory)
+struct A2NodeSmem {
+  MT19937 rng;
+  int k[A2_BMAX];       // drawn positions
+  int ok[A2_BMAX];      // index[k_c] before this batch
+  int ol[A2_BMAX];      // index[n_index-1-c] before this batch
+  int hkey[A2_HASH];    // multimap position -> draws that write it (one slot per draw)
+  int hval[A2_HASH];
+  uint32_t raw[A2_BMAX]; // raw mt19937 words of the batch; then wl[c] = most recent earlier draw writing position last_c
+  double red[32];
+  int redi[32];
+  int flag;
+  int n_live;
+};
+
+__device__ __forceinline__ unsigned a2_hash(int pos) { return ((unsigned)pos * 2654435761u) & (A2_HASH - 1); }
+// most recent draw before `c` that wrote position `pos` (-1: none)
+__device__ __forceinline__ int a2_prev_writer(const A2NodeSmem& S, int pos, int c) {
+  int best = -1;
+  unsigned h = a2_hash(pos);
+  while (true) {
+    const int key = S.hkey[h];
+    if (key == -1) break;
+    if (key == pos) { const int v = S.hval[h]; if (v < c && v > best) best = v; }
+    h = (h + 1) & (A2_HASH - 1);
+  }
+  return best;
+}
+// first draw after `c` that writes position `pos` (0x7fffffff: none)
+__device__ __forceinline__ int a2_next_writer(const A2NodeSmem& S, int pos, int c) {
+  int best = 0x7fffffff;
+  unsigned h = a2_hash(pos);
+  while (true) {
+    const int key = S.hkey[h];
+    if (key == -1) break;
+    if (key == pos) { const int v = S.hval[h]; if (v > c && v < best) best = v; }
+    h = (h + 1) & (A2_HASH - 1);
+  }
+  return best;
+}
+
+// upper bound of |k| at distance >= gap for the program's shape (+inf when the program has no decreasing bound)
+__device__ __forceinline__ double program_bound(const DevProgram* g, double gap) {
+  switch (g->shape) {
+    case BGP_SHAPE_EXPSQ: return ScaledProfile1D<BGP_SHAPE_EXPSQ>(*g).bound(gap);
+    case BGP_SHAPE_M32: return ScaledProfile1D<BGP_SHAPE_M32>(*g).bound(gap);
+    case BGP_SHAPE_M52: return ScaledProfile1D<BGP_SHAPE_M52>(*g).bound(gap);
+    case BGP_SHAPE_EXP: return ScaledProfile1D<BGP_SHAPE_EXP>(*g).bound(gap);
+    case BGP_SHAPE_PROD_EXPSQ_ES2: return ScaledProfile1D<BGP_SHAPE_PROD_EXPSQ_ES2>(*g).bound(gap);
+    case BGP_SHAPE_PROD_M32_ES2: return ScaledProfile1D<BGP_SHAPE_PROD_M32_ES2>(*g).bound(gap);
+    default: return __longlong_as_double(0x7ff0000000000000ll);
+  }
+}
+
+// Draw the next min(B, bmax, n_index) candidate rows speculatively: k_c = uniform(0, n_index-1-c) from `S.rng`
+// (advanced), swap-pop on the index list (hodlr.h:179-183):  cand[c] = A[k_c];  A[k_c] = A[n_index-1-c].
+// The positions depend on the RNG only, so the whole batch is resolved in parallel: a position's content at time c is
+// the original list entry unless an earlier draw of the batch wrote it, and what a draw writes is the content of ITS
+// "last" slot at ITS time — a chain towards earlier draws that is almost always empty (two draws of a batch touch the same
+// slot with probability ~ B / n_index).  A shared-memory multimap position -> draws gives every thread the most recent
+// earlier writer of the two slots it reads; chains are followed to their root.  The index list itself is NOT modified
+// here: a2_decide commits exactly the draws that were consumed (L[c], next[c] below), so nothing has to be undone.
+// cand[c] = row, cand_k[c] = position, words[c] = mt19937 words consumed up to and including draw c.
+//
+// Candidate-level bound culling (programs with a decreasing bound, 1-D): |residual(i, j)| <= bound(gap(x_i, node's
+// columns)) + sum_q |U(i, q)| for EVERY column (|V| <= 1: rows are normalised by their largest entry, hodlr.h:194), so a
+// candidate whose right-hand side is < 1e-14 is rejected without any evaluation; only the others ("live") get eval work.
+__device__ inline void a2_generate(const A2Args& a, A2State& st, A2NodeSmem& S, const A2Node& nd, int nid, int nb) {
+  int* __restrict__ index = a.idx_ws + nd.idx_off;
+  int* __restrict__ cand = a.cand + nd.cand_off;
+  int* __restrict__ cand_k = a.cand_k + nd.cand_off;
+  int* __restrict__ words = a.cand_words + nd.cand_off;
+  int* __restrict__ cand_L = a.cand_L + nd.cand_off;
+  int* __restrict__ cand_next = a.cand_next + nd.cand_off;
+  int* __restrict__ live = a.cand_live + nd.cand_off;
+  unsigned long long* __restrict__ cmax = a.cmax + nd.cand_off;
+  const int n_index = st.n_index;
+  const int B = min(min(st.B, nd.bmax), n_index);
+  // Lemire's multiply-shift rejects with probability s / 2^32 per draw; draw B words in parallel assuming none does and
+  // fall back to the one-word-at-a-time loop (from a saved state) in the rare batch where a rejection shows up.
+  if (threadIdx.x == 0) { S.flag = 0; S.n_live = 0; st.ncand = B; }
+  mt_fill_coop(S.rng, S.raw, B);
+  for (int c = threadIdx.x; c < B; c += blockDim.x) {
+    const uint32_t srange = (uint32_t)(n_index - c);
+    const uint64_t prod = (uint64_t)S.raw[c] * (uint64_t)srange;
+    const uint32_t low = (uint32_t)prod;
+    if (low < srange && low < (0u - srange) % srange) S.flag = 1;
+    S.k[c] = (int)(prod >> 32);
+    words[c] = c + 1;
+    cmax[c] = 0ull;
+  }
+  for (int t = threadIdx.x; t < A2_HASH; t += blockDim.x) S.hkey[t] = -1;
+  __syncthreads();
+  if (S.flag) {
+    // exact replay from the committed state (st.rng): one word at a time with the rejection loop
+    mt_copy(&S.rng, &st.rng);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int w = 0;
+      for (int c = 0; c < B; ++c) {
+        S.k[c] = mt_uniform(S.rng, (uint32_t)(n_index - c), &w);
+        words[c] = w;
+      }
+    }
+    __syncthreads();
+  }
+  for (int c = threadIdx.x; c < B; c += blockDim.x) {
+    const int pos = S.k[c];
+    S.ok[c] = index[pos];
+    S.ol[c] = index[n_index - 1 - c];
+    unsigned h = a2_hash(pos);
+    while (atomicCAS(&S.hkey[h], -1, pos) != -1) h = (h + 1) & (A2_HASH - 1);
+    S.hval[h] = c;
+  }
+  __syncthreads();
+  int* wl = reinterpret_cast<int*>(S.raw);
+  for (int c = threadIdx.x; c < B; c += blockDim.x) wl[c] = a2_prev_writer(S, n_index - 1 - c, c);
+  __syncthreads();
+  auto last_value = [&](int c) {  // content of slot n_index-1-c at time c
+    int w = wl[c];
+    while (w >= 0) { c = w; w = wl[c]; }
+    return S.ol[c];
+  };
+  const bool cull = a.vmax != nullptr;
+  const int rank = st.rank;
+  double clo = 0.0, chi = 0.0;
+  if (cull) { clo = a.node_box[2 * nid]; chi = a.node_box[2 * nid + 1]; }
+  const double* Vcols = a.Vp + (int64_t)nd.vcol * a.ld;
+  for (int c = threadIdx.x; c < B; c += blockDim.x) {
+    const int pos = S.k[c];
+    const int wk = a2_prev_writer(S, pos, c);
+    const int row = (wk < 0) ? S.ok[c] : last_value(wk);
+    cand[c] = row;
+    cand_k[c] = pos;
+    cand_L[c] = last_value(c);
+    cand_next[c] = a2_next_writer(S, pos, c);
+    bool keep = true;
+    if (cull) {
+      const double xi = a.x[nd.row0 + row];
+      double b = program_bound(a.prog, fmax(0.0, fmax(clo - xi, xi - chi)));
+      for (int q = 0; q < rank; ++q) b += fabs(__ldcg(Vcols + (int64_t)q * a.ld + nd.row0 + row));
+      keep = !(b * 1.000001 < 1e-14);  // NaN keeps the candidate
+    }
+    if (keep) live[atomicAdd(&S.n_live, 1)] = c;
+  }
+  __syncthreads();
+  // publish the evaluation work of the NEXT eval launch: one item = (column chunk, up to A2_CG * A2_ITEM_CB live candidates).
+  // In a sharded run the chunks of a node above the cut are dealt round-robin to the ranks.
+  {
+    const int n_live = S.n_live;
+    const int per_chunk = (n_live + A2_CG * A2_ITEM_CB - 1) / (A2_CG * A2_ITEM_CB);
+    int my_chunks = nd.n_cchunks;
+    const bool split = nd.is_top && a.shard_count > 1;
+    if (split) my_chunks = (nd.n_cchunks - a.shard_rank + a.shard_count - 1) / a.shard_count;
+    const int n_items = my_chunks * per_chunk;
+    int4* work_next = a.work + (int64_t)nb * a.work_cap;
+    __syncthreads();
+    if (threadIdx.x == 0) S.flag = n_items ? atomicAdd(a.work_count + nb, n_items) : 0;
+    __syncthreads();
+    const int base = S.flag;
+    for (int t = threadIdx.x; t < n_items; t += blockDim.x) {
+      const int ci = t / per_chunk, pi = t % per_chunk;
+      const int lc = split ? (a.shard_rank + ci * a.shard_count) : ci;
+      const int c0 = pi * A2_CG * A2_ITEM_CB;
+      if (base + t < a.work_cap) work_next[base + t] = make_int4(nd.cchunk0 + lc, c0, min(A2_CG * A2_ITEM_CB, n_live - c0), nid);
+    }
+  }
+  __syncthreads();
+}
 
 // ---- init: index list, RNG seed, first candidates -------------------------------------------------------------
 __global__ void __launch_bounds__(A2_THREADS) a2_init_kernel(A2Args a) {
@@ -321,8 +347,16 @@ __global__ void __launch_bounds__(A2_THREADS) a2_init_kernel(A2Args a) {
     if (threadIdx.x == 0) { st.status = 1; st.phase = A2_DONE; st.active = 0; { atomicSub(a.n_active, 1); if (nd.is_top) atomicSub(a.n_active + 1, 1); } }
     return;
   }
-  a2_generate(st, S, index, a.cand + nd.cand_off, a.cand_k + nd.cand_off, a.cand_words + nd.cand_off, nd.bmax,
-              a.cmax + nd.cand_off, nd, nid, a.work, a.work_count, a.work_cap, a.shard_rank, a.shard_count);
+  // bounding interval of the node's columns (candidate-level bound culling; 1-D programs with a distance bound only)
+  if (a.vmax) {
+    double lo = __longlong_as_double(0x7ff0000000000000ll), hi = -lo;
+    for (int n = threadIdx.x; n < nd.n_cols; n += blockDim.x) { const double xv = a.x[nd.col0 + n]; lo = fmin(lo, xv); hi = fmax(hi, xv); }
+    lo = -block_max_signed(-lo, S.red);
+    hi = block_max_signed(hi, S.red);
+    if (threadIdx.x == 0) { a.node_box[2 * nid] = lo; a.node_box[2 * nid + 1] = hi; }
+    __syncthreads();
+  }
+  a2_generate(a, st, S, nd, nid, 0);
 }
 
 // ---- eval: residual maxima of the pending candidate rows ------------------------------------------------------
@@ -351,6 +385,7 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
   const double* xr = a.x + (int64_t)nd.row0 * ndim;
   const double* xc = a.x + (int64_t)(nd.col0 + w_lo) * ndim;
   const int* cand = a.cand + nd.cand_off;
+  const int* live_list = a.cand_live + nd.cand_off;
   unsigned long long* cmax = a.cmax + nd.cand_off;
   int ncol[A2_EPT];
 #pragma unroll
@@ -358,7 +393,8 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
 
   double glo = 0.0, ghi = 0.0;
   const double* vmaxg = nullptr;
-  if constexpr (CULL) {
+  const bool cull = CULL && a.vmax != nullptr;  // runtime switch: BGP_NO_CULL runs the exhaustive scan
+  if constexpr (CULL) if (cull) {
     glo = __longlong_as_double(0x7ff0000000000000ll); ghi = -glo;
 #pragma unroll
     for (int e = 0; e < A2_EPT; ++e) { const double xv = xc[ncol[e]]; glo = fmin(glo, xv); ghi = fmax(ghi, xv); }
@@ -372,11 +408,11 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
 
   const int ncand = c_first + c_count;
   for (int cb0 = c_first; cb0 < ncand; cb0 += 32) {
-    const int myc = cb0 + lane;
-    const bool valid = myc < ncand;
+    const bool valid = cb0 + lane < ncand;
+    const int myc = valid ? live_list[cb0 + lane] : 0;  // index of the candidate in the node's batch
     const int myrow = valid ? cand[myc] : 0;
     unsigned live = __ballot_sync(0xffffffffu, valid);
-    if constexpr (CULL) {
+    if constexpr (CULL) if (cull) {
       bool keep = valid;
       if (valid) {
         const double xi = xr[myrow];
@@ -390,13 +426,14 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
     n_eval += (unsigned long long)__popc(live) * (unsigned long long)w_n;
     n_fma += (unsigned long long)__popc(live) * (unsigned long long)w_n * (unsigned long long)rank;
     while (live) {
-      int sel[A2_CG], row[A2_CG];
+      int sel[A2_CG], row[A2_CG], cidx[A2_CG];
       int ncb = 0;
 #pragma unroll
       for (int c = 0; c < A2_CG; ++c) {
         if (live) { sel[c] = __ffs(live) - 1; live &= live - 1; ncb = c + 1; }
         else sel[c] = sel[0];
         row[c] = __shfl_sync(0xffffffffu, myrow, sel[c]);
+        cidx[c] = __shfl_sync(0xffffffffu, myc, sel[c]);
       }
       double vals[A2_CG][A2_EPT];
 #pragma unroll
@@ -447,7 +484,7 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
           const unsigned long long ob = __shfl_xor_sync(0xffffffffu, bits, o);
           bits = ob > bits ? ob : bits;
         }
-        if (lane == 0 && c < ncb && bits != 0ull) atomicMax(cmax + cb0 + sel[c], bits);
+        if (lane == 0 && c < ncb && bits != 0ull) atomicMax(cmax + cidx[c], bits);
       }
     }
   }
@@ -500,8 +537,6 @@ __global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     s_winner = 0x7fffffff;
-    atomicAdd(a.stats + 0, (unsigned long long)ncand * (unsigned long long)nd.n_cols);
-    atomicAdd(a.stats + 2, (unsigned long long)ncand);
   }
   __syncthreads();
   // first candidate (sequence order) whose max |residual| over all chunks is >= 1e-14 (hodlr.h:191; a NaN also
@@ -527,17 +562,28 @@ __global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
   }
   __syncthreads();
   mt_copy(&st.rng, &S.rng);
+  // commit the swap-pops of the consumed draws 0..last: position cand_k[c] ends up with the value of the LAST consumed draw
+  // that wrote it (a2_generate left the list untouched and recorded, per draw, its value and the next writer of its slot)
+  {
+    const int last = (p != 0x7fffffff) ? p : ncand - 1;
+    if (threadIdx.x == 0) {  // consumed candidate rows: each one is a row of the block verified against the 1e-14 threshold
+      atomicAdd(a.stats + 0, (unsigned long long)(last + 1) * (unsigned long long)nd.n_cols);
+      atomicAdd(a.stats + 2, (unsigned long long)(last + 1));
+    }
+    const int* cand_L = a.cand_L + nd.cand_off;
+    const int* cand_next = a.cand_next + nd.cand_off;
+    for (int c = threadIdx.x; c <= last; c += blockDim.x)
+      if (cand_next[c] > last) index[cand_k[c]] = cand_L[c];
+  }
   __syncthreads();
   if (p != 0x7fffffff) {
     if (threadIdx.x == 0) {
-      // undo the speculative swap-pops beyond the winner, newest first
-      for (int c = ncand - 1; c > p; --c) index[cand_k[c]] = cand[c];
       st.n_index -= (p + 1);
       st.piv_i = cand[p];
       st.phase = A2_ACCEPT;  // pivot column / value follow from a2_vrow + a2_pivot
-      // next batch: as many candidates as this pivot search needed (a kernel whose rows are all usable settles at
-      // ONE candidate per step: every speculative row costs a pass over the factor panel)
-      st.B = max(1, min(st.B, p + 1));
+      // next batch: a kernel whose rows are all usable settles at ONE candidate per step (every speculative row costs a
+      // pass over the factor panel); otherwise twice what this pivot search needed
+      st.B = (p == 0) ? 1 : max(1, min(st.B, 2 * (p + 1)));
     }
     return;
   }
@@ -552,11 +598,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
   }
   __syncthreads();
   if (st.n_index == 0) return;
-  {
-    const int nb = (a.iter + 1) & 1;
-    a2_generate(st, S, index, cand, cand_k, words, nd.bmax, a.cmax + nd.cand_off, nd, nid, a.work + (int64_t)nb * a.work_cap,
-                a.work_count + nb, a.work_cap, a.shard_rank, a.shard_count);
-  }
+  a2_generate(a, st, S, nd, nid, (a.iter + 1) & 1);
 }
 
 // ---- residual of one row (vrow) or one column (ucol) of the block over a sub-chunk of A2_THREADS entries ------------
@@ -843,12 +885,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_finish_kernel(A2Args a) {
   }
   __syncthreads();
   if (s_done) return;
-  {
-    const int nb = (a.iter + 1) & 1;
-    a2_generate(st, S, a.idx_ws + nd.idx_off, a.cand + nd.cand_off, a.cand_k + nd.cand_off, a.cand_words + nd.cand_off, nd.bmax,
-                a.cmax + nd.cand_off, nd, nid, a.work + (int64_t)nb * a.work_cap, a.work_count + nb, a.work_cap, a.shard_rank,
-                a.shard_count);
-  }
+  a2_generate(a, st, S, nd, nid, (a.iter + 1) & 1);
 }
 
 // ---- dense fallback fill (hodlr.h:161-176): V = I, U = K(rows, cols) ---------------------------------------------

@@ -313,6 +313,16 @@ __device__ __forceinline__ double block_max(double v, double* red) {
   return warp_max(t);
 }
 
+__device__ __forceinline__ double block_max_signed(double v, double* red) {  // any sign (block_max pads with 0)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double t = (lane < nw) ? red[lane] : -__longlong_as_double(0x7ff0000000000000ll);
+  return warp_max(t);
+}
+
 // rng_mode BGP_RNG_REFERENCE: CTAs take tickets in pre-order and chain the single mt19937 through `chain_state`
 // (624 words + index) guarded by `chain_done[k]` flags — the pre-order dependence of hodlr.h:35,58-61 made explicit.
 __global__ void __launch_bounds__(ACA_THREADS) aca_kernel(const DevProgram* __restrict__ gprog,
