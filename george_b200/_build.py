@@ -69,7 +69,7 @@ def build(force=False, verbose=False):
         cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-c", sp, "-o", obj]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
         log = os.path.join(objdir, os.path.basename(sp) + ".ptxas.log")
-        with open(log, "w") as fh:  # tracked (register / smem / spill evidence): drop the run-to-run noise
+        with open(log, "w") as fh:  # build artefact (git-ignored); curated register / spill evidence lives in profiles/
             fh.write("".join(l for l in r.stdout.splitlines(True) if "Compile time" not in l))
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for {0}:\n{1}".format(sp, r.stdout))

@@ -483,13 +483,10 @@ static int dense_potrf(bgp_dense* h) {
 constexpr size_t DS_BWD_SMEM = sizeof(double) * ((DN_NB + DS_COLS) * (DN_NB + 1) + DN_NB + DS_MAX_RHS * DN_NB);
 
 static int dense_potrs_small(bgp_dense* h, double* X, int nrhs, int64_t ldx) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(trsv_bwd_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DS_BWD_SMEM);
+  // (the attribute is per device / context: set it on every call, it is cheap)
+  cudaFuncSetAttribute(trsv_bwd_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DS_BWD_SMEM);
     cudaFuncSetAttribute(trsv_bwd_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DS_BWD_SMEM);
     cudaFuncSetAttribute(trsv_bwd_step_kernel<DS_MAX_RHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DS_BWD_SMEM);
-    attr = true;
-  }
   const int64_t n = h->n;
   const double* L = h->d_A.p;
   cudaStream_t s = h->s;

@@ -243,11 +243,8 @@ __global__ void __launch_bounds__(GD_THREADS) gemm_dmma_kernel(const GemmDesc* _
 template <bool A_KCONTIG, bool B_KCONTIG>
 inline int gemm_dmma_launch(const GemmDesc* d_descs, int batch, int maxM, int maxN, const int* info, cudaStream_t s) {
   if (batch <= 0 || maxM <= 0 || maxN <= 0) return BGP_OK;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(gemm_dmma_kernel<A_KCONTIG, B_KCONTIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GD_SMEM_BYTES);
-    attr = true;
-  }
+  // (the attribute is per device / context: set it on every call, it is cheap)
+  cudaFuncSetAttribute(gemm_dmma_kernel<A_KCONTIG, B_KCONTIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GD_SMEM_BYTES);
   for (int b0 = 0; b0 < batch; b0 += 65535) {
     const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
     dim3 grid((maxM + GD_BM - 1) / GD_BM, (maxN + GD_BN - 1) / GD_BN, nb);

@@ -85,6 +85,7 @@ struct bgp_hodlr {
   DevBuf<uint32_t> d_chain_state;
   DevBuf<A2Node> d_a2nodes;
   DevBuf<A2State> d_a2states;
+  DevBuf<MT19937> d_a2rngs;
   DevBuf<A2EPart> d_epart;
   DevBuf<int> d_cand, d_cand_k, d_cand_words, d_cand_L, d_cand_next, d_cand_live, d_cchunk_node, d_rchunk_node, d_nactive;
   DevBuf<double> d_node_box;
@@ -135,8 +136,8 @@ static int launch_leaf_solve(bgp_hodlr* h, double* X, int64_t ldx, const int* nc
   dim3 grid(nl, (max_cols + LS_COLS - 1) / LS_COLS);
   const size_t smem = sizeof(double) * (size_t)h->max_leaf * LS_COLS;
   if (smem > 200 * 1024) { set_error("leaf size %d too large for the leaf solve kernel", h->max_leaf); return BGP_ERR_INVALID; }
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(leaf_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  // (the attribute is per device / context: set it on every call, it is cheap)
+  cudaFuncSetAttribute(leaf_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   leaf_solve_kernel<<<grid, LS_THREADS, smem, s>>>(h->d_leaves.p, h->d_L.p, X, ldx, ncols_by_depth, ncols_fixed, h->max_leaf);
   BGP_LAUNCH_CHECK();
   return BGP_OK;
@@ -172,8 +173,8 @@ static int launch_level(bgp_hodlr* h, const LevelInfo& L, double* X, int64_t ldx
   }
   {
     const size_t sbytes = sizeof(double) * (size_t)(2 * r) * (2 * r);
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(small_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
+    // (the attribute is per device / context: set it on every call, it is cheap)
+    cudaFuncSetAttribute(small_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     small_solve_kernel<<<nn, SS_THREADS, sbytes, s>>>(nd, h->d_W.p, stride, ncolsW, own_off, factor, h->d_S.p,
                                                       h->d_node_logdet.p, L.desc_off);
     BGP_LAUNCH_CHECK();
@@ -275,6 +276,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   const int ncc = (int)cchunk_node.size(), nrc = (int)rchunk_node.size();
   BGP_TRY(h->d_a2nodes.reserve(nn, s));
   BGP_TRY(h->d_a2states.reserve(nn, s));
+  BGP_TRY(h->d_a2rngs.reserve((size_t)2 * nn, s));
   BGP_TRY(h->d_cand.reserve((size_t)cand_total, s));
   BGP_TRY(h->d_cand_k.reserve((size_t)cand_total, s));
   BGP_TRY(h->d_cand_words.reserve((size_t)cand_total, s));
@@ -305,7 +307,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   BGP_CUDA(cudaMemcpyAsync(h->d_rchunk_node.p, rchunk_node.data(), sizeof(int) * nrc, cudaMemcpyHostToDevice, s));
   BGP_CUDA(cudaMemcpyAsync(h->d_nactive.p, &nn, sizeof(int), cudaMemcpyHostToDevice, s));
   A2Args a;
-  a.prog = h->d_prog.p; a.x = h->d_x.p; a.nodes = h->d_a2nodes.p; a.states = h->d_a2states.p; a.n_nodes = nn;
+  a.prog = h->d_prog.p; a.x = h->d_x.p; a.nodes = h->d_a2nodes.p; a.states = h->d_a2states.p; a.rngs = h->d_a2rngs.p; a.n_nodes = nn;
   a.Vp = h->d_V.p; a.ld = h->n; a.tol = h->opts.tol; a.seed = (uint32_t)h->opts.seed; a.exhaust_mode = h->opts.exhaust_mode;
   a.idx_ws = h->d_idx.p; a.piv_rows = h->d_piv_rows.p; a.piv_cols = h->d_piv_cols.p;
   a.cand = h->d_cand.p; a.cand_k = h->d_cand_k.p; a.cand_words = h->d_cand_words.p; a.cmax = h->d_cmax.p; a.epart = h->d_epart.p;
@@ -316,13 +318,10 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   a.work = h->d_work.p; a.work_count = h->d_work_count.p; a.work_cap = (int)work_cap; a.iter = -1;
   a.shard_rank = dist_top ? h->opts.shard_rank : 0; a.shard_count = dist_top ? h->opts.shard_count : 1;
   if (dist_top) BGP_CUDA(cudaMemcpyAsync(h->d_nactive.p + 1, &n_top, sizeof(int), cudaMemcpyHostToDevice, s));
-  static bool a2_attr = false;
-  if (!a2_attr) {
-    cudaFuncSetAttribute(a2_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A2NodeSmem));
+  // (the attribute is per device / context: set it on every call, it is cheap)
+  cudaFuncSetAttribute(a2_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A2NodeSmem));
     cudaFuncSetAttribute(a2_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A2NodeSmem));
     cudaFuncSetAttribute(a2_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A2NodeSmem));
-    a2_attr = true;
-  }
   a2_init_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), s>>>(a);
   BGP_LAUNCH_CHECK();
   int active = nn, iters = 0;
@@ -515,8 +514,8 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
     if (h->max_leaf <= 768) {
       const int ldp = lf_panel_ld(h->max_leaf);
       const size_t smem = sizeof(double) * (size_t)LF_NB * ldp;
-      static bool attr = false;
-      if (!attr) { cudaFuncSetAttribute(leaf_factor_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+      // (the attribute is per device / context: set it on every call, it is cheap)
+      cudaFuncSetAttribute(leaf_factor_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       leaf_factor_dmma_kernel<<<nl, LF_THREADS, smem, sA>>>(h->d_prog.p, h->d_x.p, h->d_diag.p, h->d_leaves.p, h->d_L.p,
                                                             h->d_leaf_logdet.p, ldp);
     } else {
@@ -585,8 +584,8 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
       int maxcap = 1;
       for (auto& L : h->levels) maxcap = std::max(maxcap, L.cap);
       const size_t smem = ((sizeof(AcaShared) + 15) & ~size_t(15)) + sizeof(double) * (size_t)maxcap;
-      static bool attr = false;
-      if (!attr) { cudaFuncSetAttribute(aca_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+      // (the attribute is per device / context: set it on every call, it is cheap)
+      cudaFuncSetAttribute(aca_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (smem > 200 * 1024) { set_error("rank capacity %d too large", maxcap); return BGP_ERR_RANK_CAPACITY; }
       aca_kernel<<<nint, ACA_THREADS, smem, sB>>>(h->d_prog.p, h->d_x.p, h->d_aca.p, nint, h->d_V.p, n, o.tol, (uint32_t)o.seed,
                                                   o.rng_mode, h->d_idx.p, h->d_piv_rows.p, h->d_piv_cols.p, h->d_aca_out.p,
@@ -770,7 +769,7 @@ void bgp_hodlr_destroy(bgp_hodlr_t* h) {
   h->d_aca_out.release(); h->d_nodes.release(); h->d_idx.release(); h->d_piv_rows.release(); h->d_piv_cols.release();
   h->lu_ws.d_nodes.release(); h->lu_ws.d_trsm.release(); h->lu_ws.d_gemm.release(); h->d_gram_desc.release(); h->d_upd_desc.release();
   h->d_ticket.release(); h->d_chain_done.release(); h->d_ncols_by_depth.release(); h->d_chain_state.release();
-  h->d_a2nodes.release(); h->d_a2states.release(); h->d_epart.release(); h->d_cand.release(); h->d_cand_k.release();
+  h->d_a2nodes.release(); h->d_a2states.release(); h->d_a2rngs.release(); h->d_epart.release(); h->d_cand.release(); h->d_cand_k.release();
   h->d_cand_words.release(); h->d_cand_L.release(); h->d_cand_next.release(); h->d_cand_live.release(); h->d_node_box.release(); h->d_cchunk_node.release(); h->d_rchunk_node.release(); h->d_nactive.release();
   h->d_inv.release(); h->d_gscratch.release(); h->d_which.release();
   h->d_vpart.release(); h->d_upart.release(); h->d_vmax.release(); h->d_cmax.release(); h->d_stats.release(); h->d_work.release(); h->d_work_count.release();
@@ -867,7 +866,7 @@ int bgp_hodlr_get_inverse(bgp_hodlr_t* h, double* out) {
     memset(c, 0, sizeof(double) * n);
     c[j] = 1.0;
   }
-  return bgp_hodlr_apply_inverse(h, out, n, n);  // symmetric: row-/column-major agree
+  return bgp_hodlr_apply_inverse(h, out, n, n);  // COLUMN-major K^-1 (symmetric only to tol: the host transposes)
 }
 
 // alpha = K^-1 r, g_p = sum_ij (alpha alpha^T - K^-1)_ij dK_ij/dtheta_p, diag(alpha alpha^T - K^-1): everything

@@ -33,6 +33,7 @@ constexpr int A2_GROUP = A2_CHUNK / (A2_THREADS / 32);  // 128 columns: what one
 constexpr int A2_NGROUP = A2_CHUNK / A2_GROUP;           // 8 groups per chunk
 static_assert(A2_NSUB * A2_THREADS == A2_CHUNK, "sub-chunks tile a chunk");
 constexpr int A2_HASH = 8192;     // open-addressing slots of the swap-pop overlay (>= 2 * A2_BMAX)
+constexpr int A2_XWORDS = 64;     // room for the extra words consumed by Lemire rejections inside one batch
 
 struct A2Node {  // static description
   int row0, n_rows, col0, n_cols;
@@ -45,9 +46,9 @@ struct A2Node {  // static description
 struct A2State {  // dynamic
   int rank, draws, n_index, fallback, status, active;
   int phase;  // 0 = candidates pending evaluation, 1 = pivot accepted (vnorm/ucol run), 2 = done
-  int B, ncand, piv_i, piv_j, _pad;
+  int B, ncand, piv_i, piv_j;
+  int end_words;  // mt19937 words drawn for the pending batch (a.rngs[2*node+1] is the stream after exactly that many)
   double pivot, norm;
-  MT19937 rng;  // committed stream
 };
 
 struct A2EPart {
@@ -121,6 +122,7 @@ struct A2Args {
   const double* x;
   const A2Node* nodes;
   A2State* states;
+  MT19937* rngs;   // [2 * node]: committed stream, [2 * node + 1]: stream after the whole pending batch
   int n_nodes;
   double* Vp;
   int64_t ld;
@@ -164,11 +166,13 @@ struct A2NodeSmem {
   int ol[A2_BMAX];      // index[n_index-1-c] before this batch
   int hkey[A2_HASH];    // multimap position -> draws that write it (one slot per draw)
   int hval[A2_HASH];
-  uint32_t raw[A2_BMAX]; // raw mt19937 words of the batch; then wl[c] = most recent earlier draw writing position last_c
+  uint32_t raw[A2_BMAX + A2_XWORDS]; // raw mt19937 words of the batch (+ the extra words of Lemire rejections); then
+                                     // wl[c] = most recent earlier draw writing position last_c
   double red[32];
   int redi[32];
   int flag;
   int n_live;
+  int extra;
 };
 
 __device__ __forceinline__ unsigned a2_hash(int pos) { return ((unsigned)pos * 2654435761u) & (A2_HASH - 1); }
@@ -233,35 +237,74 @@ __device__ inline void a2_generate(const A2Args& a, A2State& st, A2NodeSmem& S, 
   int* __restrict__ live = a.cand_live + nd.cand_off;
   unsigned long long* __restrict__ cmax = a.cmax + nd.cand_off;
   const int n_index = st.n_index;
-  const int B = min(min(st.B, nd.bmax), n_index);
-  // Lemire's multiply-shift rejects with probability s / 2^32 per draw; draw B words in parallel assuming none does and
-  // fall back to the one-word-at-a-time loop (from a saved state) in the rare batch where a rejection shows up.
-  if (threadIdx.x == 0) { S.flag = 0; S.n_live = 0; st.ncand = B; }
+  int B = min(min(st.B, nd.bmax), n_index);
+  MT19937* rng_commit = a.rngs + 2 * (int64_t)nid;
+  MT19937* rng_end = rng_commit + 1;
+  // Lemire's multiply-shift (libstdc++ uniform_int_distribution) rejects a word with probability srange / 2^32 and then
+  // takes the NEXT word of the stream for the same draw, which shifts every later draw by one word.  The batch is drawn
+  // in parallel assuming no rejection; the first draw that rejects (if any) is redone one word at a time and the tail of
+  // the batch is recomputed with the new offset.  Expected number of passes: 1 + B * n_index / 2^32.
+  if (threadIdx.x == 0) { S.flag = 0x7fffffff; S.n_live = 0; S.extra = 0; }
   mt_fill_coop(S.rng, S.raw, B);
-  for (int c = threadIdx.x; c < B; c += blockDim.x) {
-    const uint32_t srange = (uint32_t)(n_index - c);
-    const uint64_t prod = (uint64_t)S.raw[c] * (uint64_t)srange;
-    const uint32_t low = (uint32_t)prod;
-    if (low < srange && low < (0u - srange) % srange) S.flag = 1;
-    S.k[c] = (int)(prod >> 32);
-    words[c] = c + 1;
-    cmax[c] = 0ull;
+  int start = 0;
+  bool truncated = false;
+  while (true) {
+    const int extra = S.extra;
+    for (int c = start + threadIdx.x; c < B; c += blockDim.x) {
+      const uint32_t srange = (uint32_t)(n_index - c);
+      const uint64_t prod = (uint64_t)S.raw[c + extra] * (uint64_t)srange;
+      const uint32_t low = (uint32_t)prod;
+      if (low < srange && low < (0u - srange) % srange) atomicMin(&S.flag, c);
+      S.k[c] = (int)(prod >> 32);
+      words[c] = c + 1 + extra;
+      cmax[c] = 0ull;
+    }
+    __syncthreads();
+    const int c0 = S.flag;
+    if (c0 == 0x7fffffff) break;
+    // redo draw c0: words raw[c0 + extra + 1], ... until one is accepted (they were already generated for later draws)
+    if (threadIdx.x == 0) {
+      const uint32_t srange = (uint32_t)(n_index - c0);
+      const uint32_t thr = (0u - srange) % srange;
+      int e = extra;
+      int kk = -1;
+      while (e + 1 < A2_XWORDS && c0 + e + 1 < B + extra) {  // only words that exist; the rest follows below
+        ++e;
+        const uint64_t prod = (uint64_t)S.raw[c0 + e] * (uint64_t)srange;
+        if ((uint32_t)prod >= thr) { kk = (int)(prod >> 32); break; }
+      }
+      if (kk >= 0) { S.k[c0] = kk; words[c0] = c0 + 1 + e; S.extra = e; S.flag = 0x7fffffff; }
+      else S.flag = -1 - c0;  // ran out of generated words / budget: truncate the batch before this draw
+    }
+    __syncthreads();
+    if (S.flag < 0) {  // (practically unreachable) keep the draws before c0; with none left, draw c0 alone, sequentially
+      const int c0t = -1 - S.flag;
+      __syncthreads();
+      if (c0t > 0) { B = c0t; truncated = true; break; }
+      mt_copy(&S.rng, rng_commit);
+      __syncthreads();
+      if (threadIdx.x == 0) { int w = 0; S.k[0] = mt_uniform(S.rng, (uint32_t)n_index, &w); words[0] = w; cmax[0] = 0ull; S.extra = -1; }
+      __syncthreads();
+      B = 1;
+      break;
+    }
+    // the stream needs as many more words as the offset grew
+    {
+      const int grown = S.extra - extra;
+      mt_fill_coop(S.rng, S.raw + B + extra, grown);
+    }
+    start = c0 + 1;
+  }
+  // S.rng is now the stream after the words of the whole batch (unless the batch was truncated): decide copies it
+  // instead of replaying the twists when the whole batch is consumed
+  __syncthreads();
+  mt_copy(rng_end, &S.rng);
+  if (threadIdx.x == 0) {
+    st.ncand = B;
+    st.end_words = (!truncated && S.extra >= 0 && B > 0 && words[B - 1] == B + S.extra) ? B + S.extra : -1;
   }
   for (int t = threadIdx.x; t < A2_HASH; t += blockDim.x) S.hkey[t] = -1;
   __syncthreads();
-  if (S.flag) {
-    // exact replay from the committed state (st.rng): one word at a time with the rejection loop
-    mt_copy(&S.rng, &st.rng);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int w = 0;
-      for (int c = 0; c < B; ++c) {
-        S.k[c] = mt_uniform(S.rng, (uint32_t)(n_index - c), &w);
-        words[c] = w;
-      }
-    }
-    __syncthreads();
-  }
   for (int c = threadIdx.x; c < B; c += blockDim.x) {
     const int pos = S.k[c];
     S.ok[c] = index[pos];
@@ -279,34 +322,60 @@ __device__ inline void a2_generate(const A2Args& a, A2State& st, A2NodeSmem& S, 
     while (w >= 0) { c = w; w = wl[c]; }
     return S.ol[c];
   };
-  const bool cull = a.vmax != nullptr;
-  const int rank = st.rank;
-  double clo = 0.0, chi = 0.0;
-  if (cull) { clo = a.node_box[2 * nid]; chi = a.node_box[2 * nid + 1]; }
-  const double* Vcols = a.Vp + (int64_t)nd.vcol * a.ld;
   for (int c = threadIdx.x; c < B; c += blockDim.x) {
     const int pos = S.k[c];
     const int wk = a2_prev_writer(S, pos, c);
     const int row = (wk < 0) ? S.ok[c] : last_value(wk);
+    S.ok[c] = row;  // (only this thread reads ok[c])
     cand[c] = row;
     cand_k[c] = pos;
     cand_L[c] = last_value(c);
     cand_next[c] = a2_next_writer(S, pos, c);
-    bool keep = true;
-    if (cull) {
-      const double xi = a.x[nd.row0 + row];
-      double b = program_bound(a.prog, fmax(0.0, fmax(clo - xi, xi - chi)));
-      for (int q = 0; q < rank; ++q) b += fabs(__ldcg(Vcols + (int64_t)q * a.ld + nd.row0 + row));
-      keep = !(b * 1.000001 < 1e-14);  // NaN keeps the candidate
+  }
+  const bool cull = a.vmax != nullptr;
+  const int rank = st.rank;
+  if (!cull) {
+    for (int c = threadIdx.x; c < B; c += blockDim.x) live[c] = c;
+    if (threadIdx.x == 0) S.n_live = B;
+  } else {
+    const double clo = a.node_box[2 * nid], chi = a.node_box[2 * nid + 1];
+    const double* Ucol = a.Vp + (int64_t)nd.vcol * a.ld + nd.row0;
+    const double* xr = a.x + nd.row0;
+    constexpr int G = 4;  // candidates per trip: their (dependent, uncoalesced) loads are issued together
+    for (int c0 = threadIdx.x; c0 < B; c0 += G * blockDim.x) {
+      int row[G];
+      double xi[G], b[G];
+#pragma unroll
+      for (int j = 0; j < G; ++j) { const int c = c0 + j * blockDim.x; row[j] = (c < B) ? S.ok[c] : S.ok[c0]; }
+#pragma unroll
+      for (int j = 0; j < G; ++j) xi[j] = xr[row[j]];
+#pragma unroll
+      for (int j = 0; j < G; ++j) b[j] = 0.0;
+      for (int q = 0; q < rank; ++q) {
+        double u[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) u[j] = __ldcg(Ucol + (int64_t)q * a.ld + row[j]);
+#pragma unroll
+        for (int j = 0; j < G; ++j) b[j] += fabs(u[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const int c = c0 + j * blockDim.x;
+        if (c < B) {
+          const double bb = b[j] + program_bound(a.prog, fmax(0.0, fmax(clo - xi[j], xi[j] - chi)));
+          if (!(bb * 1.000001 < 1e-14)) live[atomicAdd(&S.n_live, 1)] = c;  // NaN keeps the candidate
+        }
+      }
     }
-    if (keep) live[atomicAdd(&S.n_live, 1)] = c;
   }
   __syncthreads();
   // publish the evaluation work of the NEXT eval launch: one item = (column chunk, up to A2_CG * A2_ITEM_CB live candidates).
   // In a sharded run the chunks of a node above the cut are dealt round-robin to the ranks.
   {
     const int n_live = S.n_live;
-    const int per_chunk = (n_live + A2_CG * A2_ITEM_CB - 1) / (A2_CG * A2_ITEM_CB);
+    // few live candidates: one block of A2_CG per item, so that the sweep has no sequential depth inside an item
+    const int ipc = (n_live <= 256) ? A2_CG : A2_CG * A2_ITEM_CB;
+    const int per_chunk = (n_live + ipc - 1) / ipc;
     int my_chunks = nd.n_cchunks;
     const bool split = nd.is_top && a.shard_count > 1;
     if (split) my_chunks = (nd.n_cchunks - a.shard_rank + a.shard_count - 1) / a.shard_count;
@@ -319,8 +388,8 @@ __device__ inline void a2_generate(const A2Args& a, A2State& st, A2NodeSmem& S, 
     for (int t = threadIdx.x; t < n_items; t += blockDim.x) {
       const int ci = t / per_chunk, pi = t % per_chunk;
       const int lc = split ? (a.shard_rank + ci * a.shard_count) : ci;
-      const int c0 = pi * A2_CG * A2_ITEM_CB;
-      if (base + t < a.work_cap) work_next[base + t] = make_int4(nd.cchunk0 + lc, c0, min(A2_CG * A2_ITEM_CB, n_live - c0), nid);
+      const int c0 = pi * ipc;
+      if (base + t < a.work_cap) work_next[base + t] = make_int4(nd.cchunk0 + lc, c0, min(ipc, n_live - c0), nid);
     }
   }
   __syncthreads();
@@ -341,7 +410,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_init_kernel(A2Args a) {
     st.phase = A2_SELECT; st.B = 4; st.norm = 0.0; st.pivot = 0.0; st.piv_i = 0; st.piv_j = 0; st.ncand = 0;
   }
   __syncthreads();
-  mt_copy(&st.rng, &S.rng);  // committed = state before the speculative draws
+  mt_copy(a.rngs + 2 * (int64_t)nid, &S.rng);  // committed = state before the speculative draws
   __syncthreads();
   if (nd.cap <= 0) {
     if (threadIdx.x == 0) { st.status = 1; st.phase = A2_DONE; st.active = 0; { atomicSub(a.n_active, 1); if (nd.is_top) atomicSub(a.n_active + 1, 1); } }
@@ -552,16 +621,22 @@ __global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
   }
   __syncthreads();
   const int p = s_winner;
-  // commit the stream: replay exactly the words consumed up to the winner (or the whole batch)
-  mt_copy(&S.rng, &st.rng);
-  __syncthreads();
+  // commit the stream: the words consumed up to the winner (or the whole batch).  When that is the whole batch the
+  // stream after it was saved by a2_generate; otherwise replay the words from the committed state.
   {
+    MT19937* rng_commit = a.rngs + 2 * (int64_t)nid;
     const int w = (p != 0x7fffffff) ? words[p] : (ncand > 0 ? words[ncand - 1] : 0);
-    mt_skip_coop(S.rng, w);
+    if (w == st.end_words) {
+      mt_copy(&S.rng, rng_commit + 1);
+    } else {
+      mt_copy(&S.rng, rng_commit);
+      __syncthreads();
+      mt_skip_coop(S.rng, w);
+    }
     if (threadIdx.x == 0) st.draws += w;
+    __syncthreads();
+    mt_copy(rng_commit, &S.rng);
   }
-  __syncthreads();
-  mt_copy(&st.rng, &S.rng);
   // commit the swap-pops of the consumed draws 0..last: position cand_k[c] ends up with the value of the LAST consumed draw
   // that wrote it (a2_generate left the list untouched and recorded, per draw, its value and the next writer of its slot)
   {
@@ -856,7 +931,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_finish_kernel(A2Args a) {
   }
   vdot = block_max(vdot, S.red);
   udot = block_max(udot, S.red);
-  mt_copy(&S.rng, &st.rng);
+  mt_copy(&S.rng, a.rngs + 2 * (int64_t)nid);
   if (threadIdx.x == 0) {
     a.piv_rows[nd.piv_off + rank] = st.piv_i;
     a.piv_cols[nd.piv_off + rank] = st.piv_j;

@@ -209,14 +209,20 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf_build_factor_kernel(const D
 // staged in shared memory and all threads cooperate on the substitutions.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int LS_THREADS = 256;
-constexpr int LS_COLS = 8;
+constexpr int LS_COLS = 8;   // right-hand sides per CTA = warps per CTA (one warp per column in the diagonal-block phases)
+constexpr int LS_NB = 32;    // diagonal block
 
+// Blocked substitution: per 32-column block of L, (a) the 32 x 32 diagonal block is staged in shared memory and each
+// warp solves it for one right-hand side with shuffles (no block barrier inside), (b) the rows below (forward) / the
+// columns of the block against the rows below (backward) are updated by the whole CTA with coalesced, independent loads.
+// m / 32 block steps with two barriers each instead of m dependent steps.
 __global__ void __launch_bounds__(LS_THREADS) leaf_solve_kernel(const LeafDesc* __restrict__ leaves,
                                                                 const double* __restrict__ Lbuf,
                                                                 double* __restrict__ X, int64_t ldx,
                                                                 const int* __restrict__ ncols_by_depth, int ncols_fixed,
                                                                 int max_m) {
   extern __shared__ double xs[];  // max_m x LS_COLS, column-major with leading dimension max_m
+  __shared__ double sL[LS_NB][LS_NB + 1];
   const LeafDesc lf = leaves[blockIdx.x];
   const int ncols = ncols_by_depth ? ncols_by_depth[lf.depth] : ncols_fixed;
   const int c0 = blockIdx.y * LS_COLS;
@@ -224,39 +230,89 @@ __global__ void __launch_bounds__(LS_THREADS) leaf_solve_kernel(const LeafDesc* 
   const int nc = min(LS_COLS, ncols - c0);
   const int m = lf.size;
   const double* A = Lbuf + lf.off;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int t = threadIdx.x; t < m * nc; t += LS_THREADS) {
     const int i = t % m, c = t / m;
     xs[c * max_m + i] = X[(int64_t)(c0 + c) * ldx + lf.start + i];
   }
-  __syncthreads();
-  // forward: L y = b.  Thread t handles rows i = t, t+T, ... for every column; column k of L is streamed from L2.
-  for (int k = 0; k < m; ++k) {
-    const double* Lk = A + (int64_t)k * m;
-    for (int t = threadIdx.x; t < (m - k - 1) * nc; t += LS_THREADS) {
-      const int i = k + 1 + t % (m - k - 1), c = t / (m - k - 1);
-      xs[c * max_m + i] -= Lk[i] * xs[c * max_m + k];
+  // ---- forward: L y = b (unit lower) ----
+  for (int kb = 0; kb < m; kb += LS_NB) {
+    const int nb = min(LS_NB, m - kb);
+    __syncthreads();  // xs updates of the previous block step (and the initial load) are visible; sL is free
+    for (int t = threadIdx.x; t < LS_NB * LS_NB; t += LS_THREADS) {
+      const int i = t % LS_NB, k = t / LS_NB;
+      sL[i][k] = (i < nb && k < nb && i > k) ? A[(int64_t)(kb + k) * m + kb + i] : 0.0;
     }
     __syncthreads();
+    if (warp < nc) {
+      double y = (lane < nb) ? xs[warp * max_m + kb + lane] : 0.0;
+      for (int k = 0; k < nb; ++k) {
+        const double yk = __shfl_sync(0xffffffffu, y, k);
+        if (lane > k) y -= sL[lane][k] * yk;
+      }
+      if (lane < nb) xs[warp * max_m + kb + lane] = y;
+    }
+    __syncthreads();
+    const int r0 = kb + nb;
+    for (int i = r0 + threadIdx.x; i < m; i += LS_THREADS) {
+      double acc[LS_COLS];
+#pragma unroll
+      for (int c = 0; c < LS_COLS; ++c) acc[c] = 0.0;
+      const double* Li = A + (int64_t)kb * m + i;
+#pragma unroll 8
+      for (int k = 0; k < nb; ++k) {
+        const double l = Li[(int64_t)k * m];
+#pragma unroll
+        for (int c = 0; c < LS_COLS; ++c) acc[c] += l * xs[c * max_m + kb + k];  // (columns >= nc hold stale data: never stored)
+      }
+#pragma unroll
+      for (int c = 0; c < LS_COLS; ++c) if (c < nc) xs[c * max_m + i] -= acc[c];
+    }
   }
+  __syncthreads();
   for (int t = threadIdx.x; t < m * nc; t += LS_THREADS) {
     const int i = t % m, c = t / m;
     xs[c * max_m + i] /= A[(int64_t)i * m + i];
   }
-  __syncthreads();
-  // backward: L^T z = y.  z_k = y_k - sum_{i>k} L[i][k] z_i : one warp per (k, column) dot product is too fine; do it
-  // column-oriented instead: after z_k is final, nothing else to propagate — so compute z_k by a block-wide reduction.
-  for (int k = m - 1; k >= 0; --k) {
-    const double* Lk = A + (int64_t)k * m;
-    // each warp takes columns c = warp, warp + nwarps, ...
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int c = warp; c < nc; c += LS_THREADS / 32) {
-      double s = 0.0;
-      for (int i = k + 1 + lane; i < m; i += 32) s += Lk[i] * xs[c * max_m + i];
-      s = warp_sum(s);
-      if (lane == 0) xs[c * max_m + k] -= s;
+  // ---- backward: L^T z = y ----
+  const int nblk = (m + LS_NB - 1) / LS_NB;
+  for (int b = nblk - 1; b >= 0; --b) {
+    const int kb = b * LS_NB;
+    const int nb = min(LS_NB, m - kb);
+    const int r0 = kb + nb;
+    __syncthreads();
+    for (int t = threadIdx.x; t < LS_NB * LS_NB; t += LS_THREADS) {
+      const int i = t % LS_NB, k = t / LS_NB;
+      sL[i][k] = (i < nb && k < nb && i > k) ? A[(int64_t)(kb + k) * m + kb + i] : 0.0;
+    }
+    // y_k -= sum_{i >= r0} L[i][k] z_i for the columns k of this block: warp w takes k = w, w + 8, ...
+    for (int k = warp; k < nb; k += LS_THREADS / 32) {
+      double acc[LS_COLS];
+#pragma unroll
+      for (int c = 0; c < LS_COLS; ++c) acc[c] = 0.0;
+      const double* Lk = A + (int64_t)(kb + k) * m;
+      for (int i = r0 + lane; i < m; i += 32) {
+        const double l = Lk[i];
+#pragma unroll
+        for (int c = 0; c < LS_COLS; ++c) acc[c] += l * xs[c * max_m + i];
+      }
+#pragma unroll
+      for (int c = 0; c < LS_COLS; ++c) {
+        const double sres = warp_sum(acc[c]);
+        if (lane == 0 && c < nc) xs[c * max_m + kb + k] -= sres;
+      }
     }
     __syncthreads();
+    if (warp < nc) {
+      double y = (lane < nb) ? xs[warp * max_m + kb + lane] : 0.0;
+      for (int k = nb - 1; k >= 0; --k) {
+        const double zk = __shfl_sync(0xffffffffu, y, k);
+        if (lane < k) y -= sL[k][lane] * zk;
+      }
+      if (lane < nb) xs[warp * max_m + kb + lane] = y;
+    }
   }
+  __syncthreads();
   for (int t = threadIdx.x; t < m * nc; t += LS_THREADS) {
     const int i = t % m, c = t / m;
     X[(int64_t)(c0 + c) * ldx + lf.start + i] = xs[c * max_m + i];

@@ -400,8 +400,8 @@ int kmat_general_launch(const DevProgram* dprog, int nd, const double* x1, int64
                         double* out, int64_t ld, cudaStream_t s) {
   if (n1 == 0 || n2 == 0) return BGP_OK;
   const size_t smem = kmat_smem_general(nd);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(kmat_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+  // (the attribute is per device / context: set it on every call, it is cheap)
+  cudaFuncSetAttribute(kmat_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   dim3 grid((unsigned)((n2 + KM_TJ - 1) / KM_TJ), (unsigned)((n1 + KM_TI - 1) / KM_TI));
   if (grid.y > 65535) { set_error("kmat_general: n1 too large for one launch"); return BGP_ERR_INVALID; }
   kmat_general_kernel<<<grid, KM_THREADS, smem, s>>>(dprog, x1, n1, x2, n2, out, ld);
@@ -413,8 +413,8 @@ int kmat_symmetric_launch(const DevProgram* dprog, int nd, const double* x, int6
                           double* out, int64_t ld, cudaStream_t s) {
   if (n == 0) return BGP_OK;
   const size_t smem = kmat_smem_sym(nd);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(kmat_symmetric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+  // (the attribute is per device / context: set it on every call, it is cheap)
+  cudaFuncSetAttribute(kmat_symmetric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   const unsigned nt = (unsigned)((n + KS_T - 1) / KS_T);
   if (nt > 65535) { set_error("kmat_symmetric: n too large for one launch"); return BGP_ERR_INVALID; }
   dim3 grid(nt, nt);
@@ -522,6 +522,8 @@ static int kmat_xgrad_host(const bgp_kernel_spec_t* spec, int side, const double
   DevProgram P;
   BGP_TRY(build_dev_program(spec, &P));
   const int nd = P.ndim;
+  // kernel_x_gradient keeps one ndim-vector per stack level in fixed-size local arrays (BGP_MAX_DIM entries)
+  if (nd > BGP_MAX_DIM) { set_error("input-coordinate gradients support at most %d dimensions (got %d)", BGP_MAX_DIM, nd); return BGP_ERR_INVALID; }
   if (n1 < 0 || n2 < 0) { set_error("negative size"); return BGP_ERR_INVALID; }
   if (n1 == 0 || n2 == 0) return BGP_OK;
   cudaStream_t s = 0;

@@ -129,8 +129,8 @@ int kmat_matvec_launch(const DevProgram* dprog, int nd, const double* x1, int64_
     for (int64_t c = 0; c < nrhs; ++c) BGP_CUDA(cudaMemsetAsync(out + c * ldo, 0, sizeof(double) * n1, s));
     return BGP_OK;
   }
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(kmat_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
+  // (the attribute is per device / context: set it on every call, it is cheap)
+  cudaFuncSetAttribute(kmat_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   const size_t smem = matvec_smem(nd);
   const int64_t row_tiles = (n1 + MV_TI - 1) / MV_TI;
   const int64_t nchunks = (n2 + MV_TJ - 1) / MV_TJ;

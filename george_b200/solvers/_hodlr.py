@@ -93,9 +93,11 @@ class HODLRSolver(object):
         return out.value
 
     def get_inverse(self):
+        # the library solves against a COLUMN-major identity; the HODLR inverse is symmetric only to `tol`, so hand the
+        # buffer back with the orientation the reference's Eigen -> numpy conversion has (_hodlr.cpp:193-199): M[i, j]
         out = np.empty((self._n, self._n), dtype=np.float64)
         _lib.check(self._lib.bgp_hodlr_get_inverse(self._ptr, _lib.ptr(out)))
-        return out
+        return out.T
 
     # ---- introspection (tree / index structure; not in the reference) -------------------------------------------
     def nodes(self):

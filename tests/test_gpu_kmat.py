@@ -66,3 +66,16 @@ def test_edge_shapes(gpu, oracle):
         np.testing.assert_allclose(k.get_value(x), oracle.value_symmetric(spec, x), rtol=RTOL, atol=ATOL)
     with pytest.raises(RuntimeError):
         k.get_value(rng.normal(size=(5, 2)))
+
+
+def test_x_gradient_rejects_too_many_dimensions(gpu):
+    """kernel_x_gradient keeps ndim-vectors in BGP_MAX_DIM-sized local arrays: a wider input must be rejected with a
+    ValueError, not written past them."""
+    from george_b200 import kernels as K
+    k = K.ExpSine2Kernel(gamma=1.0, log_period=0.3, ndim=10, axes=[0, 1])
+    x = np.random.default_rng(0).normal(size=(7, 10))
+    assert np.all(np.isfinite(k.get_value(x)))          # values are fine at any ndim
+    with pytest.raises(ValueError):
+        k.get_x1_gradient(x, x)
+    with pytest.raises(ValueError):
+        k.get_x2_gradient(x, x)
