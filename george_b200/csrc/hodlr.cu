@@ -29,7 +29,8 @@ int fill_identity_launch(double* A, int64_t n, cudaStream_t s);
 bool comm_ready();
 int comm_rank();
 int comm_world();
-int comm_allreduce_max_u64(unsigned long long* buf, size_t count, cudaStream_t s);
+int comm_allreduce_sum_f64(double* buf, size_t count, cudaStream_t s);
+int comm_allgather_f64(const double* send, double* recv, size_t count, cudaStream_t s);
 }
 using namespace bgp;
 
@@ -46,6 +47,11 @@ struct LevelInfo {
   int cap = 0, max_cap = 0, vcol = 0, r = 0, ucol = 0;
   int max_half = 0, grow = 0;
   int desc_off = 0;  // offset of this level's NodeDesc block
+};
+
+struct AcaGraphKey {  // everything the captured ACA loop depends on
+  A2Args a;
+  int nn, ncc, nrc, shape, grid;
 };
 
 struct bgp_hodlr {
@@ -70,6 +76,7 @@ struct bgp_hodlr {
   DevBuf<DevProgram> d_prog;
   DevBuf<double> d_x, d_yerr, d_diag, d_L, d_leaf_logdet, d_node_logdet, d_V, d_U, d_S, d_W, d_scalar, d_rhs;
   DevBuf<double> d_inv, d_gscratch;          // grad_terms: K^-1 (n x n) and the contraction partials
+  DevBuf<double> d_xsend, d_xrecv;           // sharded runs: pack / all-gather staging
   DevBuf<unsigned> d_which;
   LuWorkspace lu_ws;                         // big-rank Woodbury step (hodlr_lu.cuh)
   DevBuf<GemmDesc> d_gram_desc, d_upd_desc;
@@ -91,7 +98,11 @@ struct bgp_hodlr {
   DevBuf<double> d_node_box;
   DevBuf<unsigned long long> d_cmax, d_stats;
   DevBuf<int4> d_work;
-  DevBuf<int> d_work_count;
+  DevBuf<int> d_work_count, d_iter;
+  AcaGraphKey aca_key;
+  cudaGraph_t aca_graph = nullptr;
+  cudaGraphExec_t aca_exec = nullptr;
+  cudaStream_t sC = nullptr;  // capture stream
   bool profile = false;
   std::vector<cudaEvent_t> prof_events;
   double prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // see bgp_hodlr_last_aca_profile
@@ -127,6 +138,8 @@ static void build_tree(bgp_hodlr* h, int start, int size, int dir, int parent, i
 }
 
 static int hodlr_solve_dev(bgp_hodlr* h, double* b, int64_t nrhs, int64_t ldb, cudaStream_t s, int part);
+static int hodlr_exchange_finish(bgp_hodlr* h);
+static int hodlr_finish_top_impl(bgp_hodlr* h, bool allreduce);
 
 static int launch_leaf_solve(bgp_hodlr* h, double* X, int64_t ldx, const int* ncols_by_depth, int ncols_fixed,
                              int max_cols, cudaStream_t s) {
@@ -254,8 +267,10 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   std::vector<A2Node> hn(nn);
   std::vector<int> cchunk_node, rchunk_node;
   int64_t cand_total = 0, top_cand_total = 0;
-  // distributed scan of the nodes above the shard cut (needs the in-loop communicator; descs list those nodes first)
-  const bool dist_top = h->opts.shard_count > 1 && comm_ready() && comm_world() == h->opts.shard_count;
+  (void)top_cand_total;
+  // (the candidate scans of the nodes above the shard cut are done redundantly by every rank: with bound culling and
+  //  one-candidate batches they are cheap, and a collective inside the lock-step loop would put a latency on every step)
+  const bool dist_top = false;
   int capmax = 1;
   for (int i = 0; i < nn; ++i) {
     const AcaDesc& d = descs[i];
@@ -297,9 +312,16 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   for (int i = 0; i < nn; ++i) n_top += hn[i].is_top;
   BGP_TRY(h->d_stats.reserve(4, s));
   int64_t work_cap = 0;
-  for (int i = 0; i < nn; ++i) work_cap += (int64_t)hn[i].n_cchunks * ((hn[i].bmax + A2_CG * A2_ITEM_CB - 1) / (A2_CG * A2_ITEM_CB));
+  // items per chunk: batches of up to 256 live candidates are cut into blocks of A2_CG, larger ones into A2_CG * A2_ITEM_CB
+  for (int i = 0; i < nn; ++i) {
+    const int big = (hn[i].bmax + A2_CG * A2_ITEM_CB - 1) / (A2_CG * A2_ITEM_CB);
+    const int small = (std::min(hn[i].bmax, 256) + A2_CG - 1) / A2_CG;
+    work_cap += (int64_t)hn[i].n_cchunks * std::max(big, small);
+  }
   BGP_TRY(h->d_work.reserve((size_t)(2 * work_cap), s));
   BGP_TRY(h->d_work_count.reserve(2, s));
+  BGP_TRY(h->d_iter.reserve(1, s));
+  BGP_CUDA(cudaMemsetAsync(h->d_iter.p, 0, sizeof(int), s));
   BGP_CUDA(cudaMemsetAsync(h->d_work_count.p, 0, sizeof(int) * 2, s));
   BGP_CUDA(cudaMemsetAsync(h->d_stats.p, 0, sizeof(unsigned long long) * 4, s));
   BGP_CUDA(cudaMemcpyAsync(h->d_a2nodes.p, hn.data(), sizeof(A2Node) * nn, cudaMemcpyHostToDevice, s));
@@ -307,6 +329,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   BGP_CUDA(cudaMemcpyAsync(h->d_rchunk_node.p, rchunk_node.data(), sizeof(int) * nrc, cudaMemcpyHostToDevice, s));
   BGP_CUDA(cudaMemcpyAsync(h->d_nactive.p, &nn, sizeof(int), cudaMemcpyHostToDevice, s));
   A2Args a;
+  memset(&a, 0, sizeof(a));  // (the struct is also the key of the cached graph: no indeterminate padding)
   a.prog = h->d_prog.p; a.x = h->d_x.p; a.nodes = h->d_a2nodes.p; a.states = h->d_a2states.p; a.rngs = h->d_a2rngs.p; a.n_nodes = nn;
   a.Vp = h->d_V.p; a.ld = h->n; a.tol = h->opts.tol; a.seed = (uint32_t)h->opts.seed; a.exhaust_mode = h->opts.exhaust_mode;
   a.idx_ws = h->d_idx.p; a.piv_rows = h->d_piv_rows.p; a.piv_cols = h->d_piv_cols.p;
@@ -315,7 +338,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   a.vmax = cull ? h->d_vmax.p : nullptr;
   a.cand_L = h->d_cand_L.p; a.cand_next = h->d_cand_next.p; a.cand_live = h->d_cand_live.p; a.node_box = h->d_node_box.p;
   a.capmax = capmax; a.n_active = h->d_nactive.p; a.stats = h->d_stats.p;
-  a.work = h->d_work.p; a.work_count = h->d_work_count.p; a.work_cap = (int)work_cap; a.iter = -1;
+  a.work = h->d_work.p; a.work_count = h->d_work_count.p; a.work_cap = (int)work_cap; a.iter_ptr = h->d_iter.p;
   a.shard_rank = dist_top ? h->opts.shard_rank : 0; a.shard_count = dist_top ? h->opts.shard_count : 1;
   if (dist_top) BGP_CUDA(cudaMemcpyAsync(h->d_nactive.p + 1, &n_top, sizeof(int), cudaMemcpyHostToDevice, s));
   // (the attribute is per device / context: set it on every call, it is cheap)
@@ -326,51 +349,94 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   BGP_LAUNCH_CHECK();
   int active = nn, iters = 0;
   const int eval_grid = num_sms() * 6;  // persistent CTAs over the work list (2-3 resident per SM, a few rounds)
-  bool top_active = dist_top && n_top > 0;  // identical on every rank: the top nodes take identical decisions
-  // profiling: 7 events per lock-step iteration (before eval, then after each of the six kernels)
-  constexpr int PE = 7;
-  auto prof_mark = [&](int it, int slot) -> int {
-    if (!h->profile) return BGP_OK;
-    const size_t need = (size_t)PE * (it + 1);
-    while (h->prof_events.size() < need) {
-      cudaEvent_t e;
-      BGP_CUDA(cudaEventCreate(&e));
-      h->prof_events.push_back(e);
-    }
-    BGP_CUDA(cudaEventRecord(h->prof_events[(size_t)PE * it + slot], s));
+  // One lock-step iteration = eval -> decide -> vrow -> pivot -> vnorm|ucol -> finish -> tick.
+  auto launch_iteration = [&](cudaStream_t st, cudaGraphConditionalHandle hnd, int use_hnd, int it_prof) -> int {
+    auto mark = [&](int slot) -> int {
+      if (it_prof < 0) return BGP_OK;
+      const size_t need = (size_t)7 * (it_prof + 1);
+      while (h->prof_events.size() < need) {
+        cudaEvent_t e;
+        BGP_CUDA(cudaEventCreate(&e));
+        h->prof_events.push_back(e);
+      }
+      BGP_CUDA(cudaEventRecord(h->prof_events[(size_t)7 * it_prof + slot], st));
+      return BGP_OK;
+    };
+    BGP_TRY(mark(0));
+    a2_eval_launch(h->prog.shape, dim3(eval_grid), st, a);
+    BGP_LAUNCH_CHECK();
+    BGP_TRY(mark(1));
+    a2_decide_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), st>>>(a);
+    BGP_LAUNCH_CHECK();
+    BGP_TRY(mark(2));
+    a2_vrow_launch(h->prog.shape, dim3(ncc, A2_NSUB), st, a);
+    BGP_LAUNCH_CHECK();
+    BGP_TRY(mark(3));
+    a2_pivot_kernel<<<nn, 32, 0, st>>>(a);
+    BGP_LAUNCH_CHECK();
+    BGP_TRY(mark(4));
+    a2_vnorm_ucol_launch(h->prog.shape, dim3(ncc + nrc, A2_NSUB), st, a, ncc);
+    BGP_LAUNCH_CHECK();
+    BGP_TRY(mark(5));
+    a2_finish_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), st>>>(a);
+    BGP_LAUNCH_CHECK();
+    BGP_TRY(mark(6));
+    a2_tick_kernel<<<1, 1, 0, st>>>(a.iter_ptr, a.n_active, hnd, use_hnd);
+    BGP_LAUNCH_CHECK();
     return BGP_OK;
   };
-  while (active > 0) {
-    for (int rep = 0; rep < 8; ++rep) {
-      BGP_TRY(prof_mark(iters, 0));
-      a.iter = iters;
-      a2_eval_launch(h->prog.shape, dim3(eval_grid), s, a);
-      BGP_LAUNCH_CHECK();
-      if (top_active) BGP_TRY(comm_allreduce_max_u64(h->d_cmax.p, (size_t)top_cand_total, s));
-      BGP_TRY(prof_mark(iters, 1));
-      a2_decide_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), s>>>(a);
-      BGP_LAUNCH_CHECK();
-      BGP_TRY(prof_mark(iters, 2));
-      a2_vrow_launch(h->prog.shape, dim3(ncc, A2_NSUB), s, a);
-      BGP_LAUNCH_CHECK();
-      BGP_TRY(prof_mark(iters, 3));
-      a2_pivot_kernel<<<nn, 32, 0, s>>>(a);
-      BGP_LAUNCH_CHECK();
-      BGP_TRY(prof_mark(iters, 4));
-      a2_vnorm_ucol_launch(h->prog.shape, dim3(ncc + nrc, A2_NSUB), s, a, ncc);
-      BGP_LAUNCH_CHECK();
-      BGP_TRY(prof_mark(iters, 5));
-      a2_finish_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), s>>>(a);
-      BGP_LAUNCH_CHECK();
-      BGP_TRY(prof_mark(iters, 6));
-      iters++;
+  const bool use_graph = !h->profile && !getenv("BGP_NO_GRAPH");
+  if (use_graph) {
+    // The whole loop is ONE graph launch: a WHILE node whose body is one iteration; a2_tick_kernel keeps the condition
+    // up to date from the device-side count of active nodes.  The executable graph is cached: a hyper-parameter loop
+    // calls compute() with the same shapes and buffers over and over.
+    AcaGraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.a = a; key.nn = nn; key.ncc = ncc; key.nrc = nrc; key.shape = h->prog.shape; key.grid = eval_grid;
+    if (!h->aca_exec || memcmp(&key, &h->aca_key, sizeof(key)) != 0) {
+      if (h->aca_exec) { cudaGraphExecDestroy(h->aca_exec); h->aca_exec = nullptr; }
+      if (h->aca_graph) { cudaGraphDestroy(h->aca_graph); h->aca_graph = nullptr; }
+      BGP_CUDA(cudaGraphCreate(&h->aca_graph, 0));
+      cudaGraphConditionalHandle hnd;
+      BGP_CUDA(cudaGraphConditionalHandleCreate(&hnd, h->aca_graph, 1, cudaGraphCondAssignDefault));
+      cudaGraphNodeParams cp = {};
+      cp.type = cudaGraphNodeTypeConditional;
+      cp.conditional.handle = hnd;
+      cp.conditional.type = cudaGraphCondTypeWhile;
+      cp.conditional.size = 1;
+      cudaGraphNode_t wnode;
+      BGP_CUDA(cudaGraphAddNode(&wnode, h->aca_graph, nullptr, 0, &cp));
+      cudaGraph_t body = cp.conditional.phGraph_out[0];
+      if (!h->sC) BGP_CUDA(cudaStreamCreateWithFlags(&h->sC, cudaStreamNonBlocking));
+      BGP_CUDA(cudaStreamBeginCaptureToGraph(h->sC, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+      const int rc = launch_iteration(h->sC, hnd, 1, -1);
+      cudaGraph_t captured = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(h->sC, &captured);
+      if (rc != BGP_OK) return rc;
+      if (ce != cudaSuccess) { set_error("ACA graph capture failed: %s", cudaGetErrorString(ce)); return BGP_ERR_CUDA; }
+      BGP_CUDA(cudaGraphInstantiate(&h->aca_exec, h->aca_graph, 0));
+      h->aca_key = key;
     }
-    int act2[2] = {0, 0};
+    BGP_CUDA(cudaGraphLaunch(h->aca_exec, s));
+    int it_host = 0, act2[2] = {0, 0};
+    BGP_CUDA(cudaMemcpyAsync(&it_host, h->d_iter.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     BGP_CUDA(cudaMemcpyAsync(act2, h->d_nactive.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
     BGP_CUDA(cudaStreamSynchronize(s));
-    active = act2[0];
-    if (dist_top) top_active = act2[1] > 0;
-    if (iters > (1 << 22)) { set_error("ACA did not terminate"); return BGP_ERR_CUDA; }
+    iters = it_host;
+    g_launches.fetch_add((uint64_t)7 * (uint64_t)std::max(iters - 1, 0), std::memory_order_relaxed);  // the capture counted one iteration
+    if (act2[0] > 0) { set_error("ACA did not terminate"); return BGP_ERR_CUDA; }
+  } else {
+    while (active > 0) {
+      for (int rep = 0; rep < 8; ++rep) {
+        BGP_TRY(launch_iteration(s, 0, 0, h->profile ? iters : -1));
+        iters++;
+      }
+      int act2[2] = {0, 0};
+      BGP_CUDA(cudaMemcpyAsync(act2, h->d_nactive.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+      BGP_CUDA(cudaStreamSynchronize(s));
+      active = act2[0];
+      if (iters > (1 << 22)) { set_error("ACA did not terminate"); return BGP_ERR_CUDA; }
+    }
   }
   h->aca_iters = iters;
   {
@@ -384,7 +450,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
       for (int i = 0; i < iters; ++i)
         for (int k = 0; k < 6; ++k) {
           float ms = 0;
-          cudaEventElapsedTime(&ms, h->prof_events[(size_t)PE * i + k], h->prof_events[(size_t)PE * i + k + 1]);
+          cudaEventElapsedTime(&ms, h->prof_events[(size_t)7 * i + k], h->prof_events[(size_t)7 * i + k + 1]);
           tot[k] += ms;
         }
       h->prof[0] = tot[0];
@@ -601,6 +667,7 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
     for (int i = 0; i < nint; ++i) {
       HNode& nd = h->nodes[desc_node[i]];
       nd.rank = houts[i].rank; nd.draws = houts[i].draws; nd.fallback = houts[i].fallback;
+      if (houts[i].status == 2) { set_error("internal: ACA work list overflow"); return BGP_ERR_CUDA; }
       if (houts[i].status != 0) {
         LevelInfo& L = h->levels[nd.depth];
         if (o.rank_capacity > 0 || L.cap >= L.max_cap) {
@@ -682,7 +749,8 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
   }
   BGP_CUDA(cudaEventRecord(h->ev[3], sA));
   if (o.shard_count > 1) {
-    // the caller exchanges the top panel rows and calls bgp_hodlr_finish_top()
+    if (comm_ready() && comm_world() == o.shard_count && comm_rank() == o.shard_rank) return hodlr_exchange_finish(h);
+    // no communicator: the caller exchanges the top panel rows itself and calls bgp_hodlr_finish_top()
     BGP_CUDA(cudaStreamSynchronize(sA));
     return BGP_OK;
   }
@@ -725,10 +793,33 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
   return BGP_OK;
 }
 
+// all-gather of the shards' row slices of `cols` columns of a column-major matrix P (leading dimension ld): every rank
+// ends up with all rows.  pack -> ncclAllGather -> unpack on one stream, no host synchronisation.
+static int exchange_rows(bgp_hodlr* h, double* P, int64_t ld, int64_t cols, cudaStream_t s) {
+  if (cols <= 0) return BGP_OK;
+  const int world = h->opts.shard_count;
+  int64_t rows_pad = 0;
+  for (int64_t r : h->shard_rows) rows_pad = std::max(rows_pad, r);
+  const size_t per = (size_t)cols * rows_pad;
+  BGP_TRY(h->d_xsend.reserve(per, s));
+  BGP_TRY(h->d_xrecv.reserve(per * world, s));
+  if (h->nloc < rows_pad) BGP_CUDA(cudaMemsetAsync(h->d_xsend.p, 0, sizeof(double) * per, s));
+  pack_rows_kernel<<<1184, 256, 0, s>>>(P, ld, h->row0, h->nloc, cols, h->d_xsend.p, rows_pad);
+  BGP_LAUNCH_CHECK();
+  BGP_TRY(comm_allgather_f64(h->d_xsend.p, h->d_xrecv.p, per, s));
+  for (int sh = 0; sh < world; ++sh) {
+    if (sh == h->opts.shard_rank) continue;  // own rows are already in place
+    unpack_rows_kernel<<<1184, 256, 0, s>>>(P, ld, h->shard_row0[sh], h->shard_rows[sh], cols, h->d_xrecv.p + (size_t)sh * per, rows_pad);
+    BGP_LAUNCH_CHECK();
+  }
+  return BGP_OK;
+}
+
 // part: 0 = everything, 1 = local (leaves + levels >= cut), 2 = top (levels < cut)
 static int hodlr_solve_dev(bgp_hodlr* h, double* b, int64_t nrhs, int64_t ldb, cudaStream_t s, int part) {
   const int nlev = (int)h->levels.size();
   const int cut = h->opts.shard_count > 1 ? h->cut_depth : 0;
+  const bool native_x = part == 0 && h->opts.shard_count > 1 && comm_ready() && comm_world() == h->opts.shard_count;
   for (int64_t c0 = 0; c0 < nrhs; c0 += 64) {
     const int nc = (int)std::min<int64_t>(64, nrhs - c0);
     double* X = b + c0 * ldb;
@@ -736,10 +827,65 @@ static int hodlr_solve_dev(bgp_hodlr* h, double* b, int64_t nrhs, int64_t ldb, c
       BGP_TRY(launch_leaf_solve(h, X, ldb, nullptr, nc, nc, s));
       for (int l = nlev - 1; l >= cut; --l) BGP_TRY(launch_level(h, h->levels[l], X, ldb, nc, 0, 0, 0, nc, s));
     }
+    if (native_x) BGP_TRY(exchange_rows(h, X, ldb, nc, s));  // replicated right-hand side: every rank needs all rows
     if (part != 1) {
       for (int l = std::min(cut, nlev) - 1; l >= 0; --l) BGP_TRY(launch_level(h, h->levels[l], X, ldb, nc, 0, 0, 0, nc, s));
     }
   }
+  return BGP_OK;
+}
+
+static int64_t top_cols(const bgp_hodlr_t* h) {
+  const int cut = std::min<int>(h->cut_depth, (int)h->levels.size());
+  return cut < (int)h->levels.size() ? h->levels[cut].ucol : h->rtot;
+}
+
+// Gram / LU / log-det / update of the nodes above the shard cut (every rank does all of them: they are tiny), then the
+// log-determinant: owned leaves + owned nodes, the top nodes counted once (by shard 0); with `allreduce` the partial sums
+// are added over the ranks on the device (one double), otherwise log_det stays PARTIAL and the host sums over shards.
+static int hodlr_finish_top_impl(bgp_hodlr* h, bool allreduce) {
+  cudaStream_t s = h->sA;
+  const int nlev = (int)h->levels.size();
+  const int cut = std::min(h->cut_depth, nlev);
+  for (int l = cut - 1; l >= 0; --l) {
+    const LevelInfo& L = h->levels[l];
+    BGP_TRY(launch_level(h, L, h->d_U.p, h->n, L.ucol + L.r, L.ucol, 1, 0, L.ucol, s));
+  }
+  const int nl = (int)h->leaves.size();
+  int ndesc = 0;
+  for (auto& L : h->levels) ndesc += (int)L.nodes.size();
+  std::vector<double> ld_leaf(nl), ld_node(ndesc);
+  if (nl) BGP_CUDA(cudaMemcpyAsync(ld_leaf.data(), h->d_leaf_logdet.p, sizeof(double) * nl, cudaMemcpyDeviceToHost, s));
+  if (ndesc) BGP_CUDA(cudaMemcpyAsync(ld_node.data(), h->d_node_logdet.p, sizeof(double) * ndesc, cudaMemcpyDeviceToHost, s));
+  BGP_CUDA(cudaStreamSynchronize(s));
+  double ld = 0.0;
+  for (double v : ld_leaf) ld += v;
+  for (int l = 0; l < nlev; ++l) {
+    const LevelInfo& L = h->levels[l];
+    if (l < cut && h->opts.shard_rank != 0) continue;
+    for (size_t i = 0; i < L.nodes.size(); ++i) ld += ld_node[L.desc_off + i];
+  }
+  if (allreduce) {
+    BGP_CUDA(cudaMemcpyAsync(h->d_scalar.p, &ld, sizeof(double), cudaMemcpyHostToDevice, s));
+    BGP_TRY(comm_allreduce_sum_f64(h->d_scalar.p, 1, s));
+    BGP_CUDA(cudaMemcpyAsync(&ld, h->d_scalar.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+    BGP_CUDA(cudaStreamSynchronize(s));
+  }
+  h->log_det = ld;
+  h->computed = true;
+  return BGP_OK;
+}
+
+// sharded compute with the library's communicator: all-gather of the locally solved rows of the top-level factor panel
+// (the ONE data-path collective of compute()), then the top nodes, then the log-det all-reduce.
+static int hodlr_exchange_finish(bgp_hodlr* h) {
+  BGP_TRY(exchange_rows(h, h->d_U.p, h->n, top_cols(h), h->sA));
+  BGP_TRY(hodlr_finish_top_impl(h, true));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->t_ms[0] = ms;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]); h->t_ms[1] = ms;
+  cudaEventElapsedTime(&ms, h->ev[6], h->ev[3]); h->t_ms[2] = ms;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]); h->t_ms[3] = ms;
   return BGP_OK;
 }
 
@@ -771,9 +917,13 @@ void bgp_hodlr_destroy(bgp_hodlr_t* h) {
   h->d_ticket.release(); h->d_chain_done.release(); h->d_ncols_by_depth.release(); h->d_chain_state.release();
   h->d_a2nodes.release(); h->d_a2states.release(); h->d_a2rngs.release(); h->d_epart.release(); h->d_cand.release(); h->d_cand_k.release();
   h->d_cand_words.release(); h->d_cand_L.release(); h->d_cand_next.release(); h->d_cand_live.release(); h->d_node_box.release(); h->d_cchunk_node.release(); h->d_rchunk_node.release(); h->d_nactive.release();
-  h->d_inv.release(); h->d_gscratch.release(); h->d_which.release();
+  h->d_inv.release(); h->d_gscratch.release(); h->d_which.release(); h->d_xsend.release(); h->d_xrecv.release();
   h->d_vpart.release(); h->d_upart.release(); h->d_vmax.release(); h->d_cmax.release(); h->d_stats.release(); h->d_work.release(); h->d_work_count.release();
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+  h->d_iter.release();
+  if (h->aca_exec) cudaGraphExecDestroy(h->aca_exec);
+  if (h->aca_graph) cudaGraphDestroy(h->aca_graph);
+  if (h->sC) cudaStreamDestroy(h->sC);
   if (h->sA) {
     cudaStreamSynchronize(h->sA); cudaStreamSynchronize(h->sB);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
@@ -1008,10 +1158,6 @@ int bgp_hodlr_top_panel(bgp_hodlr_t* h, double** ptr_dev, int64_t* row0, int64_t
   return BGP_OK;
 }
 
-static int64_t top_cols(const bgp_hodlr_t* h) {
-  const int cut = std::min<int>(h->cut_depth, (int)h->levels.size());
-  return cut < (int)h->levels.size() ? h->levels[cut].ucol : h->rtot;
-}
 
 int bgp_hodlr_shard_rows(const bgp_hodlr_t* h, int32_t s, int64_t* row0, int64_t* rows) {
   if (!h || s < 0 || s >= (int)h->shard_rows.size()) { set_error("shard index out of range"); return BGP_ERR_INDEX; }
@@ -1046,31 +1192,7 @@ int bgp_hodlr_import_top(bgp_hodlr_t* h, const double* all_buf_dev, int64_t rows
 
 int bgp_hodlr_finish_top(bgp_hodlr_t* h) {
   if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
-  cudaStream_t s = h->sA;
-  const int nlev = (int)h->levels.size();
-  const int cut = std::min(h->cut_depth, nlev);
-  for (int l = cut - 1; l >= 0; --l) {
-    const LevelInfo& L = h->levels[l];
-    BGP_TRY(launch_level(h, L, h->d_U.p, h->n, L.ucol + L.r, L.ucol, 1, 0, L.ucol, s));
-  }
-  // local log-det: owned leaves + owned nodes; top nodes counted once (by shard 0)
-  const int nl = (int)h->leaves.size();
-  int ndesc = 0;
-  for (auto& L : h->levels) ndesc += (int)L.nodes.size();
-  std::vector<double> ld_leaf(nl), ld_node(ndesc);
-  if (nl) BGP_CUDA(cudaMemcpyAsync(ld_leaf.data(), h->d_leaf_logdet.p, sizeof(double) * nl, cudaMemcpyDeviceToHost, s));
-  if (ndesc) BGP_CUDA(cudaMemcpyAsync(ld_node.data(), h->d_node_logdet.p, sizeof(double) * ndesc, cudaMemcpyDeviceToHost, s));
-  BGP_CUDA(cudaStreamSynchronize(s));
-  double ld = 0.0;
-  for (double v : ld_leaf) ld += v;
-  for (int l = 0; l < nlev; ++l) {
-    const LevelInfo& L = h->levels[l];
-    if (l < cut && h->opts.shard_rank != 0) continue;
-    for (size_t i = 0; i < L.nodes.size(); ++i) ld += ld_node[L.desc_off + i];
-  }
-  h->log_det = ld;  // PARTIAL: the host sums over shards
-  h->computed = true;
-  return BGP_OK;
+  return hodlr_finish_top_impl(h, false);
 }
 
 int bgp_hodlr_solve_local_dev(bgp_hodlr_t* h, double* b_dev, int64_t nrhs, int64_t ldb) {

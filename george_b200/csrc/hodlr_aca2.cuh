@@ -152,7 +152,7 @@ struct A2Args {
   int4* work;          // eval work items (chunk, first candidate, #candidates, node), two buffers of work_cap
   int* work_count;     // [2] item counters (buffer i%2 is consumed by iteration i and refilled for i+2)
   int work_cap;
-  int iter;            // lock-step iteration number (selects the buffers)
+  int* iter_ptr;       // device counter: lock-step iteration number (selects the buffers); advanced by a2_tick_kernel
   int shard_rank, shard_count;  // multi-GPU: top nodes' column chunks are dealt round-robin to the ranks
   unsigned long long* stats;  // [0] candidate-row entries verified (pairs), [1] residual-update FMAs executed, [2] candidates,
                               // [3] entries actually evaluated by a2_eval (the rest were bounded < 1e-14 without evaluation)
@@ -382,7 +382,10 @@ __device__ inline void a2_generate(const A2Args& a, A2State& st, A2NodeSmem& S, 
     const int n_items = my_chunks * per_chunk;
     int4* work_next = a.work + (int64_t)nb * a.work_cap;
     __syncthreads();
-    if (threadIdx.x == 0) S.flag = n_items ? atomicAdd(a.work_count + nb, n_items) : 0;
+    if (threadIdx.x == 0) {
+      S.flag = n_items ? atomicAdd(a.work_count + nb, n_items) : 0;
+      if (S.flag + n_items > a.work_cap) st.status = 2;  // cannot happen (the host sizes the list for the worst case): fail loudly
+    }
     __syncthreads();
     const int base = S.flag;
     for (int t = threadIdx.x; t < n_items; t += blockDim.x) {
@@ -565,7 +568,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) a2_eval_kernel(A2Args a) {
   __shared__ DevProgram P;
   // persistent CTAs sweep the work list published by the node kernels of the previous step: perfectly balanced over
   // the chip whatever mix of nodes is still active, and no empty CTAs
-  const int buf = a.iter & 1;
+  const int buf = *a.iter_ptr & 1;
   const int n_items = min(a.work_count[buf], a.work_cap);
   const int4* items = a.work + (int64_t)buf * a.work_cap;
   if (blockIdx.x == 0 && threadIdx.x == 0) a.work_count[buf ^ 1] = 0;  // refilled by decide / finish of this iteration
@@ -673,7 +676,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
   }
   __syncthreads();
   if (st.n_index == 0) return;
-  a2_generate(a, st, S, nd, nid, (a.iter + 1) & 1);
+  a2_generate(a, st, S, nd, nid, (*a.iter_ptr + 1) & 1);
 }
 
 // ---- residual of one row (vrow) or one column (ucol) of the block over a sub-chunk of A2_THREADS entries ------------
@@ -960,7 +963,15 @@ __global__ void __launch_bounds__(A2_THREADS) a2_finish_kernel(A2Args a) {
   }
   __syncthreads();
   if (s_done) return;
-  a2_generate(a, st, S, nd, nid, (a.iter + 1) & 1);
+  a2_generate(a, st, S, nd, nid, (*a.iter_ptr + 1) & 1);
+}
+
+// ---- tick: end of a lock-step iteration.  Advances the iteration counter and, inside the captured loop (CUDA graph WHILE
+//      node), tells the graph whether another iteration is needed: no host round trip between iterations. ----
+__global__ void a2_tick_kernel(int* iter_ptr, const int* n_active, cudaGraphConditionalHandle handle, int use_handle) {
+  const int it = *iter_ptr + 1;
+  *iter_ptr = it;
+  if (use_handle) cudaGraphSetConditional(handle, (*n_active > 0 && it < (1 << 22)) ? 1u : 0u);
 }
 
 // ---- dense fallback fill (hodlr.h:161-176): V = I, U = K(rows, cols) ---------------------------------------------

@@ -8,12 +8,15 @@ The reference has no distributed code; what shards is the algorithmic independen
 
 1. factors its own sub-tree (leaves, ACAs, up-sweep) and applies it to ITS rows of the ``log2(P)`` top-level factor
    panels (whose ACAs every rank recomputes redundantly from the replicated coordinates — no communication);
-2. takes part in ONE all-gather of those locally-solved row slices (the only data-path collective; NCCL over NVLink
-   when launched with ``torchrun`` on GPUs);
+2. takes part in ONE all-gather of those locally-solved row slices — the only data-path collective of ``compute`` —
+   issued by the library itself on the solver's stream (``csrc/comm.cu``: pack kernel -> ``ncclAllGather`` -> unpack
+   kernels, no host round trip);
 3. finishes the ``P - 1`` top nodes redundantly (Gram, 2r x 2r LU, log-det, update).
 
 ``log|K|`` is an all-reduce of one double; a solve is: local sub-tree solve on the owned slice, one all-gather of the
-vector, top nodes redundantly.  ``torch.distributed`` is plumbing only; all arithmetic is in ``csrc/hodlr.cu``.
+vector, top nodes redundantly.  ``torch.distributed`` is plumbing only: it broadcasts the 128-byte NCCL unique id with
+which every rank initialises the library's communicator (``ensure_device_comm``).  All arithmetic and all data-path
+collectives are in ``csrc/hodlr.cu`` / ``csrc/comm.cu``.
 
 The exchange helpers at the bottom are backend-agnostic (tested with gloo on CPU tensors in ``tests/test_parallel.py``).
 """
@@ -69,8 +72,8 @@ _COMM_WORLD = 0
 
 
 def ensure_device_comm(group=None):
-    """Create (once) the NCCL communicator that libbgp_b200 uses INSIDE its ACA loop (``csrc/comm.cu``): rank 0 makes
-    the unique id, it is broadcast over the host's process group, every rank initialises.  Returns the world size."""
+    """Create (once) the NCCL communicator libbgp_b200 issues its data-path collectives on (``csrc/comm.cu``): rank 0
+    makes the unique id, it is broadcast over the host's process group, every rank initialises.  Returns the world size."""
     global _COMM_WORLD
     import torch
     import torch.distributed as dist
@@ -121,7 +124,6 @@ class ShardedHODLRSolver(object):
         return self._log_det
 
     def compute(self, x, yerr):
-        import torch
         import torch.distributed as dist
         from .solvers._hodlr import HODLRSolver as Native
         rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
@@ -134,68 +136,26 @@ class ShardedHODLRSolver(object):
         if self._ranges is None:
             raise ValueError("the HODLR tree (N={0}, min_size={1}) is too shallow to shard {2} ways".format(
                 self._n, self.min_size, world))
-        ensure_device_comm(self.group)  # lets the top-level candidate scans be split across the ranks
-        self.solver = Native()
+        if ensure_device_comm(self.group) != world:
+            raise RuntimeError("the library's NCCL communicator does not span the process group")
+        if self.solver is None:
+            self.solver = Native()  # one handle for the life of the solver: buffers and rank capacities are reused
+        # collective: local sub-tree, all-gather of the top panel rows, top nodes, log-det all-reduce (csrc/hodlr.cu)
         self.solver.compute(self.kernel, x, yerr, self.min_size, self.tol, self.seed, rank_capacity=self.rank_capacity,
                             shard_rank=rank, shard_count=world, exhaust=self.exhaust)
-        lib, h = self.solver._lib, self.solver._ptr
-        ptr, row0, rows, cols, ld = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
-        _lib.check(lib.bgp_hodlr_top_panel(h, C.byref(ptr), C.byref(row0), C.byref(rows), C.byref(cols), C.byref(ld)))
-        assert (row0.value, rows.value) == self._ranges[rank]
-        self._rows_pad = max(sz for _, sz in self._ranges)
-        dev = torch.device("cuda", torch.cuda.current_device())
-        if cols.value > 0 and world > 1:
-            send = torch.empty((cols.value, self._rows_pad), dtype=torch.float64, device=dev)
-            _lib.check(lib.bgp_hodlr_export_top(h, C.c_void_p(send.data_ptr()), self._rows_pad))
-            gathered = torch.empty((world, cols.value, self._rows_pad), dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(gathered.view(-1), send.view(-1), group=self.group)
-            torch.cuda.synchronize()
-            _lib.check(lib.bgp_hodlr_import_top(h, C.c_void_p(gathered.data_ptr()), self._rows_pad))
-        _lib.check(lib.bgp_hodlr_finish_top(h))
-        part = torch.tensor([self.solver.log_determinant], dtype=torch.float64, device=dev)
-        dist.all_reduce(part, group=self.group)
-        self._log_det = float(part.item())
+        self._log_det = self.solver.log_determinant
         self._computed = True
 
-    def _solve_dev(self, b):
-        """b: torch float64 CUDA tensor (n,), replicated; solved in place on every rank."""
-        import torch
-        import torch.distributed as dist
-        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
-        lib, h = self.solver._lib, self.solver._ptr
-        n = self._n
-        _lib.check(lib.bgp_hodlr_solve_local_dev(h, C.c_void_p(b.data_ptr()), 1, n))
-        if world > 1:
-            start, size = self._ranges[rank]
-            send = torch.zeros(self._rows_pad, dtype=torch.float64, device=b.device)
-            send[:size] = b[start:start + size]
-            out = torch.empty(world * self._rows_pad, dtype=torch.float64, device=b.device)
-            dist.all_gather_into_tensor(out, send, group=self.group)
-            for s, (st, sz) in enumerate(self._ranges):
-                b[st:st + sz] = out[s * self._rows_pad:s * self._rows_pad + sz]
-            torch.cuda.synchronize()
-        _lib.check(lib.bgp_hodlr_solve_top_dev(h, C.c_void_p(b.data_ptr()), 1, n))
-        return b
-
     def apply_inverse(self, y, in_place=False):
-        import torch
-        y = np.asarray(y, dtype=np.float64)
-        out = y if in_place else np.array(y)
-        cols = out.reshape(self._n, -1)
-        for c in range(cols.shape[1]):
-            b = torch.from_numpy(np.ascontiguousarray(cols[:, c])).cuda()
-            cols[:, c] = self._solve_dev(b).cpu().numpy()
-        return out.reshape(self._n, -1) if y.ndim == 1 else out
+        """Collective; ``y`` replicated on every rank."""
+        return self.solver.apply_inverse(y, in_place=in_place)
 
     def dot_solve(self, y):
-        import torch
-        y = np.ascontiguousarray(y, dtype=np.float64)
-        yd = torch.from_numpy(y).cuda()
-        b = self._solve_dev(yd.clone())
-        return float(torch.dot(yd, b).item())
+        """Collective; ``y`` replicated on every rank."""
+        return self.solver.dot_solve(y)
 
     def apply_sqrt(self, r):
         raise NotImplementedError("apply_sqrt is not implemented for the HODLRSolver")
 
     def get_inverse(self):
-        return self.apply_inverse(np.eye(self._n), in_place=True)
+        return self.solver.get_inverse()

@@ -289,9 +289,12 @@ int bgp_selftest_lu(int32_t n, int32_t nrhs, const double* S_host, double* R_hos
 int bgp_selftest_gemm(int32_t a_kcontig, int32_t b_kcontig, int32_t m, int32_t n, int32_t k, const double* A_host,
                       int64_t lda, const double* B_host, int64_t ldb, double* C_host, int64_t ldc, int32_t atomic_add);
 
-/* Multi-GPU exchange step: after the local sub-tree is factored, the rows this
- * shard owns of the shared top-level factor panel are exported, all-gathered by the host
- * (torch.distributed / NCCL), imported, and the top nodes are finished redundantly.
+/* Multi-GPU.  With a communicator (bgp_comm_init) whose size and rank match opts.shard_count /
+ * opts.shard_rank, bgp_hodlr_compute[_dev] is COLLECTIVE and complete: local sub-tree, all-gather of the rows this shard
+ * owns of the top-level factor panel (pack kernel -> ncclAllGather -> unpack kernels on the solver's stream), the nodes
+ * above the cut, log-det all-reduce; apply_inverse / dot_solve are collective too (replicated right-hand side, one
+ * all-gather of the locally solved slices).  WITHOUT a communicator the same steps are exposed one by one so that a host
+ * can run the exchange itself: the rows are exported, all-gathered by the host, imported, and the top nodes finished.
  *   bgp_hodlr_top_panel(h, &ptr_dev, &rows, &cols, &ld): device pointer to the (N x cols) column-major panel
  *   bgp_hodlr_finish_top(h): Gram/LU/log-det/update of the nodes above the shard cut.               */
 int bgp_hodlr_top_panel(bgp_hodlr_t* h, double** ptr_dev, int64_t* row0, int64_t* rows, int64_t* cols, int64_t* ld);
@@ -302,11 +305,9 @@ int bgp_hodlr_import_top(bgp_hodlr_t* h, const double* all_buf_dev, int64_t rows
 /* row range [row0, row0+rows) owned by shard `s` (same on every shard; -1 rows if the tree cannot be cut) */
 int bgp_hodlr_shard_rows(const bgp_hodlr_t* h, int32_t s, int64_t* row0, int64_t* rows);
 int bgp_hodlr_finish_top(bgp_hodlr_t* h);
-/* NCCL communicator used INSIDE the ACA loop of a sharded compute: the candidate scan of the nodes above the shard cut
- * is split across ranks by column chunk and the per-candidate maxima are MAX-all-reduced every iteration.  Rank 0 makes
- * a unique id (128 bytes), the host broadcasts it (torch.distributed), every rank calls bgp_comm_init.  `nccl_path`
- * may be NULL: the library already loaded in the process (torch's libnccl.so.2) is used.  Without a communicator a
- * sharded compute recomputes the top-level scans redundantly on every rank. */
+/* The library's NCCL communicator (one per process).  Rank 0 makes a unique id (128 bytes), the host broadcasts it over
+ * whatever it has (torch.distributed, MPI, a file), every rank calls bgp_comm_init.  `nccl_path` may be NULL: the library
+ * already loaded in the process (torch's libnccl.so.2) is used, else libnccl.so.2 is dlopen'ed. */
 int bgp_comm_unique_id(void* out128, const char* nccl_path);
 int bgp_comm_init(const void* id128, int rank, int world, const char* nccl_path);
 int bgp_comm_destroy(void);
