@@ -96,6 +96,7 @@ struct bgp_hodlr {
   DevBuf<A2EPart> d_epart;
   DevBuf<int> d_cand, d_cand_k, d_cand_words, d_cand_L, d_cand_next, d_cand_live, d_cchunk_node, d_rchunk_node, d_nactive;
   DevBuf<double> d_node_box;
+  DevBuf<double2> d_cand_xu;
   DevBuf<unsigned long long> d_cmax, d_stats;
   DevBuf<int4> d_work;
   DevBuf<int> d_work_count, d_iter;
@@ -306,7 +307,10 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   BGP_TRY(h->d_vpart.reserve((size_t)ncc * A2_NSUB * (capmax + 1), s));
   BGP_TRY(h->d_upart.reserve((size_t)nrc * A2_NSUB * (capmax + 1), s));
   const bool cull = shape_has_bound(h->prog.shape) && !getenv("BGP_NO_CULL");  // BGP_NO_CULL: exhaustive scan (tests compare both)
-  if (cull) BGP_TRY(h->d_vmax.reserve((size_t)ncc * A2_NGROUP * capmax, s));
+  if (cull) {
+    BGP_TRY(h->d_vmax.reserve((size_t)ncc * A2_NGROUP, s));
+    BGP_TRY(h->d_cand_xu.reserve((size_t)cand_total, s));
+  }
   BGP_TRY(h->d_nactive.reserve(2, s));
   int n_top = 0;
   for (int i = 0; i < nn; ++i) n_top += hn[i].is_top;
@@ -319,10 +323,10 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
     work_cap += (int64_t)hn[i].n_cchunks * std::max(big, small);
   }
   BGP_TRY(h->d_work.reserve((size_t)(2 * work_cap), s));
-  BGP_TRY(h->d_work_count.reserve(2, s));
+  BGP_TRY(h->d_work_count.reserve(4, s));  // [0..1] item counters, [2..3] consumption cursors
   BGP_TRY(h->d_iter.reserve(1, s));
   BGP_CUDA(cudaMemsetAsync(h->d_iter.p, 0, sizeof(int), s));
-  BGP_CUDA(cudaMemsetAsync(h->d_work_count.p, 0, sizeof(int) * 2, s));
+  BGP_CUDA(cudaMemsetAsync(h->d_work_count.p, 0, sizeof(int) * 4, s));
   BGP_CUDA(cudaMemsetAsync(h->d_stats.p, 0, sizeof(unsigned long long) * 4, s));
   BGP_CUDA(cudaMemcpyAsync(h->d_a2nodes.p, hn.data(), sizeof(A2Node) * nn, cudaMemcpyHostToDevice, s));
   BGP_CUDA(cudaMemcpyAsync(h->d_cchunk_node.p, cchunk_node.data(), sizeof(int) * ncc, cudaMemcpyHostToDevice, s));
@@ -336,16 +340,17 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   a.cand = h->d_cand.p; a.cand_k = h->d_cand_k.p; a.cand_words = h->d_cand_words.p; a.cmax = h->d_cmax.p; a.epart = h->d_epart.p;
   a.cchunk_node = h->d_cchunk_node.p; a.rchunk_node = h->d_rchunk_node.p; a.vpart = h->d_vpart.p; a.upart = h->d_upart.p;
   a.vmax = cull ? h->d_vmax.p : nullptr;
+  a.cand_xu = cull ? h->d_cand_xu.p : nullptr;
   a.cand_L = h->d_cand_L.p; a.cand_next = h->d_cand_next.p; a.cand_live = h->d_cand_live.p; a.node_box = h->d_node_box.p;
   a.capmax = capmax; a.n_active = h->d_nactive.p; a.stats = h->d_stats.p;
-  a.work = h->d_work.p; a.work_count = h->d_work_count.p; a.work_cap = (int)work_cap; a.iter_ptr = h->d_iter.p;
+  a.work = h->d_work.p; a.work_count = h->d_work_count.p; a.work_cursor = h->d_work_count.p + 2; a.work_cap = (int)work_cap; a.iter_ptr = h->d_iter.p;
   a.shard_rank = dist_top ? h->opts.shard_rank : 0; a.shard_count = dist_top ? h->opts.shard_count : 1;
   if (dist_top) BGP_CUDA(cudaMemcpyAsync(h->d_nactive.p + 1, &n_top, sizeof(int), cudaMemcpyHostToDevice, s));
   // (the attribute is per device / context: set it on every call, it is cheap)
   cudaFuncSetAttribute(a2_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A2NodeSmem));
     cudaFuncSetAttribute(a2_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A2NodeSmem));
     cudaFuncSetAttribute(a2_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A2NodeSmem));
-  a2_init_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), s>>>(a);
+  a2_init_kernel<<<nn, A2_NODE_THREADS, sizeof(A2NodeSmem), s>>>(a);
   BGP_LAUNCH_CHECK();
   int active = nn, iters = 0;
   const int eval_grid = num_sms() * 6;  // persistent CTAs over the work list (2-3 resident per SM, a few rounds)
@@ -366,7 +371,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
     a2_eval_launch(h->prog.shape, dim3(eval_grid), st, a);
     BGP_LAUNCH_CHECK();
     BGP_TRY(mark(1));
-    a2_decide_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), st>>>(a);
+    a2_decide_kernel<<<nn, A2_NODE_THREADS, sizeof(A2NodeSmem), st>>>(a);
     BGP_LAUNCH_CHECK();
     BGP_TRY(mark(2));
     a2_vrow_launch(h->prog.shape, dim3(ncc, A2_NSUB), st, a);
@@ -378,7 +383,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
     a2_vnorm_ucol_launch(h->prog.shape, dim3(ncc + nrc, A2_NSUB), st, a, ncc);
     BGP_LAUNCH_CHECK();
     BGP_TRY(mark(5));
-    a2_finish_kernel<<<nn, A2_THREADS, sizeof(A2NodeSmem), st>>>(a);
+    a2_finish_kernel<<<nn, A2_NODE_THREADS, sizeof(A2NodeSmem), st>>>(a);
     BGP_LAUNCH_CHECK();
     BGP_TRY(mark(6));
     a2_tick_kernel<<<1, 1, 0, st>>>(a.iter_ptr, a.n_active, hnd, use_hnd);
@@ -916,7 +921,7 @@ void bgp_hodlr_destroy(bgp_hodlr_t* h) {
   h->lu_ws.d_nodes.release(); h->lu_ws.d_trsm.release(); h->lu_ws.d_gemm.release(); h->d_gram_desc.release(); h->d_upd_desc.release();
   h->d_ticket.release(); h->d_chain_done.release(); h->d_ncols_by_depth.release(); h->d_chain_state.release();
   h->d_a2nodes.release(); h->d_a2states.release(); h->d_a2rngs.release(); h->d_epart.release(); h->d_cand.release(); h->d_cand_k.release();
-  h->d_cand_words.release(); h->d_cand_L.release(); h->d_cand_next.release(); h->d_cand_live.release(); h->d_node_box.release(); h->d_cchunk_node.release(); h->d_rchunk_node.release(); h->d_nactive.release();
+  h->d_cand_words.release(); h->d_cand_L.release(); h->d_cand_next.release(); h->d_cand_live.release(); h->d_node_box.release(); h->d_cand_xu.release(); h->d_cchunk_node.release(); h->d_rchunk_node.release(); h->d_nactive.release();
   h->d_inv.release(); h->d_gscratch.release(); h->d_which.release(); h->d_xsend.release(); h->d_xrecv.release();
   h->d_vpart.release(); h->d_upart.release(); h->d_vmax.release(); h->d_cmax.release(); h->d_stats.release(); h->d_work.release(); h->d_work_count.release();
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);

@@ -24,6 +24,8 @@ namespace bgp {
 
 constexpr int A2_CHUNK = 1024;    // rows / columns per work item
 constexpr int A2_THREADS = 256;
+constexpr int A2_NODE_THREADS = 1024;  // per-node kernels (init / decide / finish): one CTA per node whose work is a chain
+                                       // of short, latency-bound phases over up to A2_BMAX candidates — more threads per phase
 constexpr int A2_EPT = A2_CHUNK / A2_THREADS;  // elements per thread
 constexpr int A2_CG = 4;          // candidates evaluated together (register blocking)
 constexpr int A2_ITEM_CB = 8;      // candidate blocks (of A2_CG rows) per eval work item
@@ -145,12 +147,14 @@ struct A2Args {
   const int* rchunk_node;
   double* vpart;   // per column sub-chunk: [(chunk * A2_NSUB + sub) * (capmax + 1)] : vn2 then dots[k]
   double* upart;   // per row sub-chunk
-  double* vmax;    // per (column chunk, 128-column group, factor k): max |V(j, k)| over the group  [(chunk*8+g)*capmax + k]
-                   // (bound culling of a2_eval; nullptr when the program has no distance bound)
+  double* vmax;    // per (column chunk, 128-column group): max over the factors q and the group's columns j of |V(j, q)|
+                   // [chunk * 8 + g]  (bound culling of a2_eval; nullptr when the program has no distance bound)
+  double2* cand_xu;  // per candidate: (coordinate of its row, sum_q |U(row, q)|), written by a2_generate for a2_eval
   int capmax;
   int* n_active;
   int4* work;          // eval work items (chunk, first candidate, #candidates, node), two buffers of work_cap
   int* work_count;     // [2] item counters (buffer i%2 is consumed by iteration i and refilled for i+2)
+  int* work_cursor;    // [2] next (item, group) unit of the buffer being consumed (a2_eval pulls work dynamically)
   int work_cap;
   int* iter_ptr;       // device counter: lock-step iteration number (selects the buffers); advanced by a2_tick_kernel
   int shard_rank, shard_count;  // multi-GPU: top nodes' column chunks are dealt round-robin to the ranks
@@ -363,7 +367,10 @@ __device__ inline void a2_generate(const A2Args& a, A2State& st, A2NodeSmem& S, 
         const int c = c0 + j * blockDim.x;
         if (c < B) {
           const double bb = b[j] + program_bound(a.prog, fmax(0.0, fmax(clo - xi[j], xi[j] - chi)));
-          if (!(bb * 1.000001 < 1e-14)) live[atomicAdd(&S.n_live, 1)] = c;  // NaN keeps the candidate
+          if (!(bb * 1.000001 < 1e-14)) {  // NaN keeps the candidate
+            live[atomicAdd(&S.n_live, 1)] = c;
+            a.cand_xu[nd.cand_off + c] = make_double2(xi[j], b[j]);
+          }
         }
       }
     }
@@ -399,7 +406,7 @@ __device__ inline void a2_generate(const A2Args& a, A2State& st, A2NodeSmem& S, 
 }
 
 // ---- init: index list, RNG seed, first candidates -------------------------------------------------------------
-__global__ void __launch_bounds__(A2_THREADS) a2_init_kernel(A2Args a) {
+__global__ void __launch_bounds__(A2_NODE_THREADS) a2_init_kernel(A2Args a) {
   extern __shared__ __align__(16) unsigned char a2_smem_raw[];
   A2NodeSmem& S = *reinterpret_cast<A2NodeSmem*>(a2_smem_raw);
   const int nid = blockIdx.x;
@@ -438,7 +445,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_init_kernel(A2Args a) {
 //
 // Bound culling (CULL; 1-D inputs, programs whose |k| has a decreasing bound in the distance).  The only consumer of the
 // maxima is the test  max_j |residual(i, j)| >= 1e-14  (hodlr.h:191).  For a candidate row i and this warp's 128 columns
-//     |residual(i, j)| <= |k(x_i, x_j)| + sum_q |U(i, q)| |V(j, q)| <= bound(gap(x_i, group)) + sum_q |U(i, q)| vmax(group, q)
+//     |residual(i, j)| <= |k(x_i, x_j)| + sum_q |U(i, q)| |V(j, q)| <= bound(gap(x_i, group)) + (sum_q |U(i, q)|) vmax(group)
 // and when the right-hand side (with a 1e-6 relative margin for the rounding of both sides) is below 1e-14 the group
 // cannot change the outcome of that test, so it is not evaluated.  Lane c works out the bound of candidate c; the warp
 // then sweeps only the surviving candidates.  The decisions — hence pivots, ranks and RNG draws — are exactly those of
@@ -446,10 +453,10 @@ __global__ void __launch_bounds__(A2_THREADS) a2_init_kernel(A2Args a) {
 // (Matern / squared-exponential tails: everything farther than a few dozen length scales from the block's corner).
 template <class KFn, bool CULL>
 __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, int rank, int chunk, int c_first,
-                                             int c_count, int ndim, KFn fn, unsigned long long& n_eval,
+                                             int c_count, int ndim, KFn fn, int warp, unsigned long long& n_eval,
                                              unsigned long long& n_fma) {
   const int lc = chunk - nd.cchunk0;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int w_lo = lc * A2_CHUNK + warp * A2_GROUP;  // first column of this warp
   const int w_n = min(A2_GROUP, nd.n_cols - w_lo);
   if (w_n <= 0) return;
@@ -466,6 +473,7 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
   double glo = 0.0, ghi = 0.0;
   const double* vmaxg = nullptr;
   const bool cull = CULL && a.vmax != nullptr;  // runtime switch: BGP_NO_CULL runs the exhaustive scan
+  double vg = 0.0;
   if constexpr (CULL) if (cull) {
     glo = __longlong_as_double(0x7ff0000000000000ll); ghi = -glo;
 #pragma unroll
@@ -475,7 +483,8 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
       glo = fmin(glo, __shfl_xor_sync(0xffffffffu, glo, o));
       ghi = fmax(ghi, __shfl_xor_sync(0xffffffffu, ghi, o));
     }
-    vmaxg = a.vmax + ((int64_t)chunk * A2_NGROUP + warp) * a.capmax;
+    vmaxg = a.vmax + ((int64_t)chunk * A2_NGROUP + warp);
+    vg = __ldcg(vmaxg);
   }
 
   const int ncand = c_first + c_count;
@@ -487,10 +496,9 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
     if constexpr (CULL) if (cull) {
       bool keep = valid;
       if (valid) {
-        const double xi = xr[myrow];
-        const double gap = fmax(0.0, fmax(glo - xi, xi - ghi));
-        double b = fn.bound(gap);
-        for (int k = 0; k < rank; ++k) b += fabs(__ldcg(Vcols + (int64_t)k * a.ld + nd.row0 + myrow)) * vmaxg[k];
+        const double2 xu = __ldcg(a.cand_xu + nd.cand_off + myc);  // (x_i, sum_q |U(i, q)|) from a2_generate
+        const double gap = fmax(0.0, fmax(glo - xu.x, xu.x - ghi));
+        const double b = fn.bound(gap) + xu.y * vg;
         keep = !(b * 1.000001 < 1e-14);  // NaN keeps the candidate
       }
       live = __ballot_sync(0xffffffffu, keep);
@@ -579,12 +587,22 @@ __global__ void __launch_bounds__(A2_THREADS, 2) a2_eval_kernel(A2Args a) {
   const auto fn = ShapeEval<SHAPE>::make(&P, a.prog);
   constexpr bool CULL = shape_has_bound(SHAPE);
   unsigned long long n_eval = 0ull, n_fma = 0ull;
-  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-    const int4 w = items[it];
+  // work unit = (item, 128-column group); every WARP pulls its next unit from a global cursor: items differ wildly in cost
+  // (fully culled ... 32 candidate rows to evaluate), a static deal leaves most of the chip idle behind the few heavy ones
+  int* cursor = a.work_cursor + buf;
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.work_cursor[buf ^ 1] = 0;
+  const int n_units = n_items * A2_NGROUP;
+  while (true) {
+    int u = 0;
+    if ((threadIdx.x & 31) == 0) u = atomicAdd(cursor, 1);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u >= n_units) break;
+    const int4 w = items[u / A2_NGROUP];
+    const int grp = u % A2_NGROUP;
     const A2Node& nd = a.nodes[w.w];
     const int rank = a.states[w.w].rank;
-    if constexpr (SHAPE == BGP_SHAPE_GENERIC) a2_eval_body<decltype(fn), false>(a, nd, rank, w.x, w.y, w.z, P.ndim, fn, n_eval, n_fma);
-    else a2_eval_body<decltype(fn), CULL>(a, nd, rank, w.x, w.y, w.z, 1, fn, n_eval, n_fma);
+    if constexpr (SHAPE == BGP_SHAPE_GENERIC) a2_eval_body<decltype(fn), false>(a, nd, rank, w.x, w.y, w.z, P.ndim, fn, grp, n_eval, n_fma);
+    else a2_eval_body<decltype(fn), CULL>(a, nd, rank, w.x, w.y, w.z, 1, fn, grp, n_eval, n_fma);
   }
   if ((threadIdx.x & 31) == 0 && n_eval) { atomicAdd(a.stats + 3, n_eval); atomicAdd(a.stats + 1, n_fma); }
 }
@@ -593,7 +611,7 @@ inline void a2_eval_launch(int shape, dim3 grid, cudaStream_t s, const A2Args& a
 }
 
 // ---- decide: first usable candidate wins; commit the RNG / index list up to it ----------------------------------
-__global__ void __launch_bounds__(A2_THREADS) a2_decide_kernel(A2Args a) {
+__global__ void __launch_bounds__(A2_NODE_THREADS) a2_decide_kernel(A2Args a) {
   extern __shared__ __align__(16) unsigned char a2_smem_raw[];
   A2NodeSmem& S = *reinterpret_cast<A2NodeSmem*>(a2_smem_raw);
   __shared__ int s_winner;
@@ -832,7 +850,8 @@ __device__ __forceinline__ void a2_vnorm_body(const A2Args& a, int chunk, int su
   if (a.vmax && threadIdx.x < 2) {
     const int g = threadIdx.x;
     const double m = fmax(fmax(red[16 + 4 * g], red[17 + 4 * g]), fmax(red[18 + 4 * g], red[19 + 4 * g]));
-    a.vmax[((int64_t)chunk * A2_NGROUP + sub * 2 + g) * a.capmax + rank] = m;
+    double* slot = a.vmax + ((int64_t)chunk * A2_NGROUP + sub * 2 + g);
+    if (rank == 0 || m > *slot || m != m) *slot = m;  // running maximum over the factors (first factor: overwrite)
   }
   double* part = a.vpart + ((int64_t)chunk * A2_NSUB + sub) * (a.capmax + 1);
   if (threadIdx.x == 0) part[0] = vn2;
@@ -906,7 +925,7 @@ inline void a2_vnorm_ucol_launch(int shape, dim3 grid, cudaStream_t s, const A2A
 }
 
 // ---- finish: stopping rule (hodlr.h:202-214), next candidates -----------------------------------------------------
-__global__ void __launch_bounds__(A2_THREADS) a2_finish_kernel(A2Args a) {
+__global__ void __launch_bounds__(A2_NODE_THREADS) a2_finish_kernel(A2Args a) {
   extern __shared__ __align__(16) unsigned char a2_smem_raw[];
   A2NodeSmem& S = *reinterpret_cast<A2NodeSmem*>(a2_smem_raw);
   __shared__ int s_done;

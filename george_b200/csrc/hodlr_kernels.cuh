@@ -616,7 +616,7 @@ constexpr int GT_THREADS = 256;
 constexpr int GT_ROWS = 64;   // rows per shared-memory slab
 constexpr int GT_TQ = 32;     // W rows (V columns) per CTA pass
 constexpr int GT_TC = 32;     // W cols (X columns) per CTA
-constexpr int GT_CHUNK = 2048;  // rows per CTA
+constexpr int GT_CHUNK = 512;   // rows per CTA (8 slabs: the top levels get enough CTAs to hide the slab latency)
 
 __global__ void __launch_bounds__(GT_THREADS) gram_tn_kernel(const NodeDesc* __restrict__ nodes,
                                                              const double* __restrict__ Vp, int64_t ldv,
