@@ -68,19 +68,28 @@ __device__ __forceinline__ void mt_copy(MT19937* dst, const MT19937* src) {
   for (int i = threadIdx.x; i < (int)(sizeof(MT19937) / 4); i += blockDim.x) d[i] = s[i];
 }
 
-// cooperative twist of the whole state (3 dependent phases of <= 227 independent elements + the last word)
+// cooperative twist of the whole state: 3 dependent phases of <= 227 independent elements + the last word.  Element i
+// needs the OLD mt[i + 1], which the neighbouring thread overwrites in the same phase: every phase computes into
+// registers, synchronises, then stores.
 __device__ __forceinline__ void mt_twist_coop(MT19937& g) {
-  auto step = [&](int i, uint32_t a, uint32_t b, uint32_t m) {
+  auto value = [&](uint32_t a, uint32_t b, uint32_t m) {
     const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
-    g.mt[i] = m ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    return m ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
   };
-  for (int i = threadIdx.x; i < 227; i += blockDim.x) step(i, g.mt[i], g.mt[i + 1], g.mt[i + 397]);
-  __syncthreads();
-  for (int i = 227 + threadIdx.x; i < 454; i += blockDim.x) step(i, g.mt[i], g.mt[i + 1], g.mt[i - 227]);
-  __syncthreads();
-  for (int i = 454 + threadIdx.x; i < 623; i += blockDim.x) step(i, g.mt[i], g.mt[i + 1], g.mt[i - 227]);
-  __syncthreads();
-  if (threadIdx.x == 0) { step(623, g.mt[623], g.mt[0], g.mt[396]); g.idx = 0; }
+  auto phase = [&](int lo, int hi, int moff) {  // elements [lo, hi), partner mt[i + moff]
+    for (int base = lo; base < hi; base += blockDim.x) {  // (one trip for blockDim >= 227)
+      const int i = base + threadIdx.x;
+      uint32_t v = 0;
+      if (i < hi) v = value(g.mt[i], g.mt[i + 1], g.mt[i + moff]);
+      __syncthreads();
+      if (i < hi) g.mt[i] = v;
+      __syncthreads();
+    }
+  };
+  phase(0, 227, 397);
+  phase(227, 454, -227);
+  phase(454, 623, -227);
+  if (threadIdx.x == 0) { g.mt[623] = value(g.mt[623], g.mt[0], g.mt[396]); g.idx = 0; }
   __syncthreads();
 }
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
