@@ -20,6 +20,8 @@ for name, kernel, n, ms, exhaust in [
     ("m32", 1.0 * kernels.Matern32Kernel(1.0), 16384, 256, "lowrank"),
     ("odd", 1.0 * kernels.ExpSquaredKernel(1.0), 8191, 100, "dense"),
     ("m32dense", 1.0 * kernels.Matern32Kernel(1.0), 6000, 100, "dense"),   # big-rank (blocked LU) top levels
+    ("cfg5", 1.0 * kernels.ExpSquaredKernel(1.0) + 0.5 * kernels.ExpSine2Kernel(gamma=1.0, log_period=np.log(3.0)), 32768, 100, "lowrank"),
+    ("m32big", 1.0 * kernels.Matern32Kernel(1.0), 262144, 256, "lowrank"),
 ]:
     rng = np.random.default_rng(1234)
     x = np.sort(rng.uniform(0, 10 * n / 1000, n)); yerr = 0.1 * np.ones(n); y = np.sin(x) + 0.1 * rng.normal(size=n)
