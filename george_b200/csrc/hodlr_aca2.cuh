@@ -50,6 +50,7 @@ struct A2State {  // dynamic
   int phase;  // 0 = candidates pending evaluation, 1 = pivot accepted (vnorm/ucol run), 2 = done
   int B, ncand, piv_i, piv_j;
   int end_words;  // mt19937 words drawn for the pending batch (a.rngs[2*node+1] is the stream after exactly that many)
+  int deferred;   // the pending batch is ONE live candidate whose acceptance test is left to a2_vrow / a2_pivot
   double pivot, norm;
 };
 
@@ -59,7 +60,11 @@ struct A2EPart {
   int _pad;
 };
 
-enum { A2_SELECT = 0, A2_ACCEPT = 1, A2_DONE = 2 };
+enum { A2_SELECT = 0, A2_ACCEPT = 1, A2_DONE = 2, A2_LATE_REJECT = 3 };
+// A2_LATE_REJECT: a one-candidate batch is not evaluated by a2_eval at all — a2_vrow computes that row anyway when it is
+// accepted, and its arg-max IS the acceptance test (hodlr.h:191); a2_pivot turns the provisional accept into a reject when
+// |pivot| < 1e-14 and a2_finish draws the next batch.  One pass over the factor panel less per step for kernels whose rows
+// are all usable (the high-rank regime, where a step is bound by exactly those passes).
 
 // cooperative 625-word copy of an mt19937 state (all threads of the CTA; caller synchronises)
 __device__ __forceinline__ void mt_copy(MT19937* dst, const MT19937* src) {
@@ -388,7 +393,10 @@ __device__ inline void a2_generate(const A2Args& a, A2State& st, A2NodeSmem& S, 
   // publish the evaluation work of the NEXT eval launch: one item = (column chunk, up to A2_CG * A2_ITEM_CB live candidates).
   // In a sharded run the chunks of a node above the cut are dealt round-robin to the ranks.
   {
-    const int n_live = S.n_live;
+    int n_live = S.n_live;
+    const bool defer = (B == 1 && n_live == 1);
+    if (threadIdx.x == 0) st.deferred = defer ? 1 : 0;
+    if (defer) n_live = 0;  // no eval work: see A2_LATE_REJECT
     // few live candidates: one block of A2_CG per item, so that the sweep has no sequential depth inside an item
     const int ipc = (n_live <= 256) ? A2_CG : A2_CG * A2_ITEM_CB;
     const int per_chunk = (n_live + ipc - 1) / ipc;
@@ -639,8 +647,12 @@ __global__ void __launch_bounds__(A2_NODE_THREADS) a2_decide_kernel(A2Args a) {
   }
   __syncthreads();
   // first candidate (sequence order) whose max |residual| over all chunks is >= 1e-14 (hodlr.h:191; a NaN also
-  // leaves the reference's loop): the per-candidate maxima were reduced across chunks by atomicMax in a2_eval
-  {
+  // leaves the reference's loop): the per-candidate maxima were reduced across chunks by atomicMax in a2_eval.
+  // A deferred one-candidate batch is accepted provisionally (a2_pivot applies the test to the row a2_vrow computes).
+  const bool deferred = st.deferred != 0;
+  if (deferred) {
+    if (threadIdx.x == 0) { s_winner = 0; atomicAdd(a.stats + 3, (unsigned long long)nd.n_cols); }
+  } else {
     const unsigned long long* cmax = a.cmax + nd.cand_off;
     int mine = 0x7fffffff;
     for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
@@ -820,7 +832,36 @@ __global__ void __launch_bounds__(32) a2_pivot_kernel(A2Args a) {
     if (oi == 0x7fffffff) continue;
     if (bidx == 0x7fffffff || fabs(ov) > fabs(bval) || (fabs(ov) == fabs(bval) && oi < bidx) || (ov != ov && !(bval != bval))) { bval = ov; bidx = oi; }
   }
-  if (lane == 0) { st.piv_j = bidx; st.pivot = bval; }
+  if (lane == 0) {
+    st.piv_j = bidx; st.pivot = bval;
+    if (st.deferred && fabs(bval) < 1e-14) st.phase = A2_LATE_REJECT;  // hodlr.h:191 (a NaN pivot leaves the loop: accepted)
+  }
+}
+
+// partial dot products  part[1 + q] = sum_n P[q][n] * s_vec[n]  over this CTA's `cnt` entries, for q < rank: warp w takes
+// q = w, w + W, ... four at a time (their loads are independent: 32 in flight per lane)
+__device__ __forceinline__ void a2_partial_dots(const double* __restrict__ pbase, int64_t ld, int rank, const double* s_vec,
+                                                int cnt, double* __restrict__ part) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int W = A2_THREADS / 32, QU = 4;
+  for (int q0 = warp * QU; q0 < rank; q0 += W * QU) {
+    double acc[QU];
+#pragma unroll
+    for (int u = 0; u < QU; ++u) acc[u] = 0.0;
+    for (int n = lane; n < cnt; n += 32) {
+      const double sv = s_vec[n];
+      double pv[QU];
+#pragma unroll
+      for (int u = 0; u < QU; ++u) pv[u] = (q0 + u < rank) ? pbase[(int64_t)(q0 + u) * ld + n] : 0.0;
+#pragma unroll
+      for (int u = 0; u < QU; ++u) acc[u] += pv[u] * sv;
+    }
+#pragma unroll
+    for (int u = 0; u < QU; ++u) {
+      const double r = warp_sum(acc[u]);
+      if (lane == 0 && q0 + u < rank) part[1 + q0 + u] = r;
+    }
+  }
 }
 
 // ---- vnorm: normalise the stored row residual (hodlr.h:194), partial ||v||^2 and V_prev^T v, group maxima ------------
@@ -864,13 +905,7 @@ __device__ __forceinline__ void a2_vnorm_body(const A2Args& a, int chunk, int su
   }
   double* part = a.vpart + ((int64_t)chunk * A2_NSUB + sub) * (a.capmax + 1);
   if (threadIdx.x == 0) part[0] = vn2;
-  for (int k = warp; k < rank; k += A2_THREADS / 32) {
-    const double* vk = Vcols + (int64_t)k * a.ld + nd.col0 + c_lo;
-    double s = 0.0;
-    for (int n = lane; n < c_n; n += 32) s += vk[n] * s_v[n];
-    s = warp_sum(s);
-    if (lane == 0) part[1 + k] = s;
-  }
+  a2_partial_dots(Vcols + nd.col0 + c_lo, a.ld, rank, s_v, c_n, part);
 }
 
 // ---- ucol: column residual -> panel column `rank` (row part), partial ||u||^2 and U_prev^T u --------------------
@@ -917,14 +952,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_vnorm_ucol_kernel(A2Args a, int
   un2 = block_sum(un2, red);
   double* part = a.upart + ((int64_t)chunk * A2_NSUB + sub) * (a.capmax + 1);
   if (threadIdx.x == 0) part[0] = un2;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int k = warp; k < rank; k += A2_THREADS / 32) {
-    const double* uk = Vcols + (int64_t)k * a.ld + nd.row0 + r_lo;
-    double s = 0.0;
-    for (int n2 = lane; n2 < r_n; n2 += 32) s += uk[n2] * s_u[n2];
-    s = warp_sum(s);
-    if (lane == 0) part[1 + k] = s;
-  }
+  a2_partial_dots(Vcols + nd.row0 + r_lo, a.ld, rank, s_u, r_n, part);
 }
 inline void a2_vrow_launch(int shape, dim3 grid, cudaStream_t s, const A2Args& a) {
   BGP_SHAPE_SWITCH(shape, (a2_vrow_kernel<SHAPE><<<grid, A2_THREADS, 0, s>>>(a)));
@@ -940,7 +968,28 @@ __global__ void __launch_bounds__(A2_NODE_THREADS) a2_finish_kernel(A2Args a) {
   __shared__ int s_done;
   const int nid = blockIdx.x;
   A2State& st = a.states[nid];
-  if (st.phase != A2_ACCEPT || !st.active) return;
+  if (!st.active) return;
+  if (st.phase == A2_LATE_REJECT) {  // the deferred candidate failed the pivot test: same bookkeeping as a rejected batch
+    const A2Node nd = a.nodes[nid];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      st.B = min(4 * st.B, A2_BMAX);
+      if (st.n_index == 0) {
+        st.fallback = 1;
+        st.phase = A2_DONE; st.active = 0;
+        { atomicSub(a.n_active, 1); if (nd.is_top) atomicSub(a.n_active + 1, 1); }
+      } else {
+        st.phase = A2_SELECT;
+      }
+    }
+    __syncthreads();
+    if (st.phase == A2_DONE) return;
+    mt_copy(&S.rng, a.rngs + 2 * (int64_t)nid);
+    __syncthreads();
+    a2_generate(a, st, S, nd, nid, (*a.iter_ptr + 1) & 1);
+    return;
+  }
+  if (st.phase != A2_ACCEPT) return;
   const A2Node nd = a.nodes[nid];
   const int rank = st.rank;
   double vn2 = 0.0, un2 = 0.0;
