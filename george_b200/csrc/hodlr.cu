@@ -42,9 +42,21 @@ struct HNode {
   int top = 0;     // sharding: node above the shard cut (finished after the exchange)
 };
 
+// Factor panels.  A level owned by one shard only ever touches that shard's rows, so its panels hold
+// nloc rows (leading dimension nloc) and are addressed with GLOBAL row indices through a base pointer shifted by the
+// shard's first row; the levels above the shard cut span all N rows.  Single-GPU runs have only the "local" set (all rows).
+struct PanelSet {
+  DevBuf<double> V, U;
+  int64_t ld = 0, row_off = 0;
+  int vcols = 0, ucols = 0;
+  double* vbase() const { return V.p - row_off; }
+  double* ubase() const { return U.p - row_off; }
+};
+
 struct LevelInfo {
   std::vector<int> nodes;  // pre-order ids of the internal nodes at this depth handled here
-  int cap = 0, max_cap = 0, vcol = 0, r = 0, ucol = 0;
+  int set = 1;             // 0: level above the shard cut (panel set `top`), 1: owned level (panel set `loc`)
+  int cap = 0, max_cap = 0, vcol = 0, r = 0, ucol = 0;  // vcol / ucol: first column of the level in ITS panel set
   int max_half = 0, grow = 0;
   int desc_off = 0;  // offset of this level's NodeDesc block
 };
@@ -74,7 +86,9 @@ struct bgp_hodlr {
   std::vector<int64_t> shard_row0, shard_rows;
 
   DevBuf<DevProgram> d_prog;
-  DevBuf<double> d_x, d_yerr, d_diag, d_L, d_leaf_logdet, d_node_logdet, d_V, d_U, d_S, d_W, d_scalar, d_rhs;
+  DevBuf<double> d_x, d_yerr, d_diag, d_L, d_leaf_logdet, d_node_logdet, d_S, d_W, d_scalar, d_rhs;
+  PanelSet top, loc;
+  const PanelSet& pset(const LevelInfo& L) const { return L.set == 0 ? top : loc; }
   DevBuf<double> d_inv, d_gscratch;          // grad_terms: K^-1 (n x n) and the contraction partials
   DevBuf<double> d_xsend, d_xrecv;           // sharded runs: pack / all-gather staging
   DevBuf<unsigned> d_which;
@@ -182,7 +196,7 @@ static int launch_level(bgp_hodlr* h, const LevelInfo& L, double* X, int64_t ldx
   const int max_nh = L.max_half + 1;
   {
     dim3 grid((max_nh + GT_CHUNK - 1) / GT_CHUNK, nn * 2, (ncolsW + GT_TC - 1) / GT_TC);
-    gram_tn_kernel<<<grid, GT_THREADS, 0, s>>>(nd, h->d_V.p, h->n, X, ldx, ncolsW, h->d_W.p, stride);
+    gram_tn_kernel<<<grid, GT_THREADS, 0, s>>>(nd, h->pset(L).vbase(), h->pset(L).ld, X, ldx, ncolsW, h->d_W.p, stride);
     BGP_LAUNCH_CHECK();
   }
   {
@@ -195,7 +209,7 @@ static int launch_level(bgp_hodlr* h, const LevelInfo& L, double* X, int64_t ldx
   }
   if (col_hi > col_lo) {
     dim3 grid((max_nh + UP_ROWS - 1) / UP_ROWS, nn * 2, (col_hi - col_lo + UP_TC - 1) / UP_TC);
-    update_nn_kernel<<<grid, UP_THREADS, 0, s>>>(nd, h->d_U.p, h->n, X, ldx, col_lo, col_hi, h->d_W.p, stride, 0);
+    update_nn_kernel<<<grid, UP_THREADS, 0, s>>>(nd, h->pset(L).ubase(), h->pset(L).ld, X, ldx, col_lo, col_hi, h->d_W.p, stride, 0);
     BGP_LAUNCH_CHECK();
   }
   return BGP_OK;
@@ -206,7 +220,7 @@ static int launch_level_big(bgp_hodlr* h, const LevelInfo& L, double* X, int64_t
   const int nn = (int)L.nodes.size();
   const int r = L.r, n2 = 2 * r;
   const int64_t stride = (int64_t)n2 * ncolsW;
-  const int64_t ldv = h->n, ldu = h->n;
+  const int64_t ldv = h->pset(L).ld, ldu = h->pset(L).ld;
   double* W = h->d_W.p;
   constexpr int KCHUNK = 4096;  // rows per split-K slice of the Gram product
   std::vector<LuNode> lun(nn);
@@ -224,7 +238,7 @@ static int launch_level_big(bgp_hodlr* h, const LevelInfo& L, double* X, int64_t
       max_nh = std::max(max_nh, nh);
       for (int k0 = 0; k0 < nh; k0 += KCHUNK) {  // W_h (r x ncolsW) += V_h^T X_h
         GemmDesc g;
-        g.A = h->d_V.p + (int64_t)L.vcol * ldv + rs + k0; g.lda = ldv;   // A'(q, i) = V[i + q ldv]
+        g.A = h->pset(L).vbase() + (int64_t)L.vcol * ldv + rs + k0; g.lda = ldv;   // A'(q, i) = V[i + q ldv]
         g.B = X + rs + k0; g.ldb = ldx;                                   // B'(i, c) = X[i + c ldx]
         g.C = Wn + (hh ? 0 : r); g.ldc = n2;
         g.M = r; g.N = ncolsW; g.K = std::min(KCHUNK, nh - k0); g.mode = GD_ATOMIC_ADD;
@@ -232,7 +246,7 @@ static int launch_level_big(bgp_hodlr* h, const LevelInfo& L, double* X, int64_t
       }
       if (col_hi > col_lo) {  // X_h[:, col_lo:col_hi] -= U_h T_h
         GemmDesc g;
-        g.A = h->d_U.p + (int64_t)L.ucol * ldu + rs; g.lda = ldu;        // A'(i, q) = U[i + q ldu]
+        g.A = h->pset(L).ubase() + (int64_t)L.ucol * ldu + rs; g.lda = ldu;        // A'(i, q) = U[i + q ldu]
         g.B = Wn + (hh ? r : 0) + (int64_t)col_lo * n2; g.ldb = n2;       // B'(q, c) = T[q + c 2r]
         g.C = X + rs + (int64_t)col_lo * ldx; g.ldc = ldx;
         g.M = nh; g.N = col_hi - col_lo; g.K = r; g.mode = GD_SUB;
@@ -278,6 +292,11 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
     A2Node& a = hn[i];
     a.row0 = d.row0; a.n_rows = d.n_rows; a.col0 = d.col0; a.n_cols = d.n_cols;
     a.vcol = d.vcol; a.cap = d.cap; a.pre_id = d.pre_id; a.node = d.node;
+    {
+      const PanelSet& ps = h->pset(h->levels[h->nodes[d.pre_id].depth]);
+      a.ld = ps.ld;
+      a.vbase = ps.vbase() + (int64_t)d.vcol * ps.ld;
+    }
     a.idx_off = d.idx_off; a.piv_off = d.piv_off;
     a.cchunk0 = (int)cchunk_node.size(); a.n_cchunks = (d.n_cols + A2_CHUNK - 1) / A2_CHUNK;
     a.rchunk0 = (int)rchunk_node.size(); a.n_rchunks = (d.n_rows + A2_CHUNK - 1) / A2_CHUNK;
@@ -335,7 +354,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   A2Args a;
   memset(&a, 0, sizeof(a));  // (the struct is also the key of the cached graph: no indeterminate padding)
   a.prog = h->d_prog.p; a.x = h->d_x.p; a.nodes = h->d_a2nodes.p; a.states = h->d_a2states.p; a.rngs = h->d_a2rngs.p; a.n_nodes = nn;
-  a.Vp = h->d_V.p; a.ld = h->n; a.tol = h->opts.tol; a.seed = (uint32_t)h->opts.seed; a.exhaust_mode = h->opts.exhaust_mode;
+  a.tol = h->opts.tol; a.seed = (uint32_t)h->opts.seed; a.exhaust_mode = h->opts.exhaust_mode;
   a.idx_ws = h->d_idx.p; a.piv_rows = h->d_piv_rows.p; a.piv_cols = h->d_piv_cols.p;
   a.cand = h->d_cand.p; a.cand_k = h->d_cand_k.p; a.cand_words = h->d_cand_words.p; a.cmax = h->d_cmax.p; a.epart = h->d_epart.p;
   a.cchunk_node = h->d_cchunk_node.p; a.rchunk_node = h->d_rchunk_node.p; a.vpart = h->d_vpart.p; a.upart = h->d_upart.p;
@@ -541,6 +560,9 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
   }
   while (!h->levels.empty() && h->levels.back().nodes.empty()) h->levels.pop_back();
   const int nlev = (int)h->levels.size();
+  for (int l = 0; l < nlev; ++l) h->levels[l].set = (o.shard_count > 1 && l < cut) ? 0 : 1;
+  h->top.ld = n; h->top.row_off = 0;
+  h->loc.ld = h->nloc; h->loc.row_off = h->row0;
 
   // ---- capacities: start from rank_capacity (default 128) per level; levels that overflow are grown and the ACA
   //      stage is repeated (deterministic: the per-node / chained streams restart from the same seeds) ----
@@ -605,9 +627,10 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
   int nint = 0;
   BGP_CUDA(cudaStreamWaitEvent(sB, h->ev[0], 0));
   for (int attempt = 0;; ++attempt) {
-    int vcols = 0;
-    for (auto& L : h->levels) { L.vcol = vcols; vcols += L.cap; }
-    h->vcols = vcols;
+    int vcols_set[2] = {0, 0};
+    for (auto& L : h->levels) { L.vcol = vcols_set[L.set]; vcols_set[L.set] += L.cap; }
+    h->top.vcols = vcols_set[0]; h->loc.vcols = vcols_set[1];
+    h->vcols = vcols_set[0] + vcols_set[1];
     hdesc.clear(); desc_node.clear();
     h->piv_off.assign(h->nodes.size(), -1);
     idx_total = 0; piv_total = 0; nint = 0;
@@ -636,7 +659,22 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
     std::vector<AcaDesc> hdesc_sorted(nint);
     for (int i = 0; i < nint; ++i) hdesc_sorted[i] = hdesc[order[i]];
 
-    BGP_TRY(h->d_V.reserve((size_t)n * std::max(vcols, 1), sB));
+    {
+      // a capacity that no longer fits: give the old block back to the driver before asking for the larger one (the pool
+      // keeps freed blocks cached, and a 2x larger request cannot reuse them: without the trim both would be resident)
+      const size_t need_top = (size_t)n * std::max(h->top.vcols, 1), need_loc = (size_t)h->nloc * std::max(h->loc.vcols, 1);
+      if ((h->top.V.p && h->top.V.n < need_top) || (h->loc.V.p && h->loc.V.n < need_loc)) {
+        if (h->top.V.n < need_top) h->top.V.release();
+        if (h->loc.V.n < need_loc) h->loc.V.release();
+        h->top.U.release(); h->loc.U.release();
+        BGP_CUDA(cudaStreamSynchronize(sA)); BGP_CUDA(cudaStreamSynchronize(sB));
+        cudaMemPool_t pool; int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+      }
+      BGP_TRY(h->top.V.reserve(need_top, sB));
+      BGP_TRY(h->loc.V.reserve(need_loc, sB));
+    }
     BGP_TRY(h->d_aca.reserve(std::max(nint, 1), sB));
     BGP_TRY(h->d_aca_out.reserve(std::max(nint, 1), sB));
     BGP_TRY(h->d_idx.reserve((size_t)std::max<int64_t>(idx_total, 1), sB));
@@ -658,7 +696,7 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
       // (the attribute is per device / context: set it on every call, it is cheap)
       cudaFuncSetAttribute(aca_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (smem > 200 * 1024) { set_error("rank capacity %d too large", maxcap); return BGP_ERR_RANK_CAPACITY; }
-      aca_kernel<<<nint, ACA_THREADS, smem, sB>>>(h->d_prog.p, h->d_x.p, h->d_aca.p, nint, h->d_V.p, n, o.tol, (uint32_t)o.seed,
+      aca_kernel<<<nint, ACA_THREADS, smem, sB>>>(h->d_prog.p, h->d_x.p, h->d_aca.p, nint, h->loc.vbase(), h->loc.ld, o.tol, (uint32_t)o.seed,
                                                   o.rng_mode, h->d_idx.p, h->d_piv_rows.p, h->d_piv_cols.p, h->d_aca_out.p,
                                                   h->d_ticket.p, h->d_chain_state.p, h->d_chain_done.p, o.exhaust_mode);
       BGP_LAUNCH_CHECK();
@@ -693,7 +731,7 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
     for (auto& L : h->levels) if (L.grow > L.cap) L.cap = L.grow;
     if (attempt > 16) { set_error("ACA capacity growth did not converge"); return BGP_ERR_RANK_CAPACITY; }
   }
-  int rtot = 0, ndesc = 0;
+  int rtot_set[2] = {0, 0}, ndesc = 0, ndesc_top = 0;
   int64_t s_total = 0;
   size_t w_need = 1;
   std::vector<NodeDesc> hnd;
@@ -701,8 +739,8 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
     LevelInfo& L = h->levels[l];
     L.r = 0;
     for (int id : L.nodes) L.r = std::max(L.r, h->nodes[id].rank);
-    L.ucol = rtot;
-    rtot += L.r;
+    L.ucol = rtot_set[L.set];
+    rtot_set[L.set] += L.r;
     L.desc_off = ndesc;
     for (int id : L.nodes) {
       const HNode& nd = h->nodes[id];
@@ -712,18 +750,24 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
       s_total += (int64_t)(2 * L.r) * (2 * L.r) + 2 * L.r + 2;
       hnd.push_back(d);
       ndesc++;
+      if (L.set == 0) ndesc_top++;
     }
     w_need = std::max(w_need, (size_t)L.nodes.size() * 2 * (size_t)L.r * (size_t)(L.ucol + L.r));
   }
+  h->top.ucols = rtot_set[0]; h->loc.ucols = rtot_set[1];
+  const int rtot = rtot_set[0] + rtot_set[1];
   h->rtot = rtot;
-  // per-depth number of ancestor columns a leaf (or node) at that depth sees
-  std::vector<int> ncols_by_depth(max_depth + 2, rtot);
-  for (int dpt = 0; dpt <= max_depth + 1; ++dpt) ncols_by_depth[dpt] = dpt < nlev ? h->levels[dpt].ucol : rtot;
+  // per-depth number of LOCAL ancestor columns a leaf (or node) at that depth sees (levels above the cut live in the top
+  // panel set and receive this shard's sub-tree inverse in a separate pass, below)
+  std::vector<int> ncols_by_depth(max_depth + 2, h->loc.ucols);
+  for (int dpt = 0; dpt <= max_depth + 1; ++dpt)
+    ncols_by_depth[dpt] = dpt < nlev ? (h->levels[dpt].set == 1 ? h->levels[dpt].ucol : 0) : h->loc.ucols;
 
   BGP_CUDA(cudaEventRecord(h->ev[6], sA));  // ranks known, both streams drained up to here: the up-sweep starts
   BGP_TRY(h->d_nodes.reserve(std::max(ndesc, 1), sA));
   BGP_TRY(h->d_node_logdet.reserve(std::max(ndesc, 1), sA));
-  BGP_TRY(h->d_U.reserve((size_t)n * std::max(rtot, 1), sA));
+  BGP_TRY(h->top.U.reserve((size_t)n * std::max(h->top.ucols, 1), sA));
+  BGP_TRY(h->loc.U.reserve((size_t)h->nloc * std::max(h->loc.ucols, 1), sA));
   BGP_TRY(h->d_S.reserve((size_t)std::max<int64_t>(s_total, 1), sA));
   // solve() needs 2*r*nrhs per node; keep room for 64 right-hand sides per batch
   for (auto& L : h->levels) w_need = std::max(w_need, (size_t)L.nodes.size() * 2 * (size_t)L.r * 64);
@@ -736,22 +780,31 @@ static int hodlr_compute_dev_impl(bgp_hodlr* h, const bgp_kernel_spec_t* spec, c
     BGP_CUDA(cudaMemcpyAsync(h->d_nodes.p, hnd.data(), sizeof(NodeDesc) * ndesc, cudaMemcpyHostToDevice, sA));
     h->h_nodes = hnd;
     BGP_CUDA(cudaMemsetAsync(h->d_node_logdet.p, 0, sizeof(double) * ndesc, sA));
-    int rmax = 0;
-    for (auto& L : h->levels) rmax = std::max(rmax, L.r);
-    if (rmax > 0) {
-      dim3 grid(ndesc, rmax);
-      finalize_panels_kernel<<<grid, 256, 0, sA>>>(h->d_nodes.p, h->d_V.p, n, h->d_U.p, n);
+    // the levels above the cut come first in the descriptor list: one launch per panel set
+    int rmax_set[2] = {0, 0};
+    for (auto& L : h->levels) rmax_set[L.set] = std::max(rmax_set[L.set], L.r);
+    if (ndesc_top > 0 && rmax_set[0] > 0) {
+      finalize_panels_kernel<<<dim3(ndesc_top, rmax_set[0]), 256, 0, sA>>>(h->d_nodes.p, h->top.vbase(), h->top.ld, h->top.ubase(), h->top.ld);
+      BGP_LAUNCH_CHECK();
+    }
+    if (ndesc > ndesc_top && rmax_set[1] > 0) {
+      finalize_panels_kernel<<<dim3(ndesc - ndesc_top, rmax_set[1]), 256, 0, sA>>>(h->d_nodes.p + ndesc_top, h->loc.vbase(), h->loc.ld,
+                                                                                  h->loc.ubase(), h->loc.ld);
       BGP_LAUNCH_CHECK();
     }
   }
 
   // ---- up-sweep (stream A; leaves are already ordered before this on the same stream) ----
-  if (rtot > 0) BGP_TRY(launch_leaf_solve(h, h->d_U.p, n, h->d_ncols_by_depth.p, 0, rtot, sA));
+  // (1) the owned sub-tree against its own (local) ancestor columns
+  if (h->loc.ucols > 0) BGP_TRY(launch_leaf_solve(h, h->loc.ubase(), h->loc.ld, h->d_ncols_by_depth.p, 0, h->loc.ucols, sA));
   const int stop_level = (o.shard_count > 1) ? h->cut_depth : 0;
   for (int l = nlev - 1; l >= stop_level; --l) {
     const LevelInfo& L = h->levels[l];
-    BGP_TRY(launch_level(h, L, h->d_U.p, n, L.ucol + L.r, L.ucol, 1, 0, L.ucol, sA));
+    BGP_TRY(launch_level(h, L, h->loc.ubase(), h->loc.ld, L.ucol + L.r, L.ucol, 1, 0, L.ucol, sA));
   }
+  // (2) sharded: the factored sub-tree applied to this shard's rows of the top-level factor columns (hodlr.h:95-102 for
+  //     the ancestors above the cut) — the same kernels as a solve with the top panel as right-hand sides
+  if (o.shard_count > 1 && h->top.ucols > 0) BGP_TRY(hodlr_solve_dev(h, h->top.U.p, h->top.ucols, n, sA, 1));
   BGP_CUDA(cudaEventRecord(h->ev[3], sA));
   if (o.shard_count > 1) {
     if (comm_ready() && comm_world() == o.shard_count && comm_rank() == o.shard_rank) return hodlr_exchange_finish(h);
@@ -842,7 +895,8 @@ static int hodlr_solve_dev(bgp_hodlr* h, double* b, int64_t nrhs, int64_t ldb, c
 
 static int64_t top_cols(const bgp_hodlr_t* h) {
   const int cut = std::min<int>(h->cut_depth, (int)h->levels.size());
-  return cut < (int)h->levels.size() ? h->levels[cut].ucol : h->rtot;
+  (void)cut;
+  return h->top.ucols;
 }
 
 // Gram / LU / log-det / update of the nodes above the shard cut (every rank does all of them: they are tiny), then the
@@ -854,7 +908,7 @@ static int hodlr_finish_top_impl(bgp_hodlr* h, bool allreduce) {
   const int cut = std::min(h->cut_depth, nlev);
   for (int l = cut - 1; l >= 0; --l) {
     const LevelInfo& L = h->levels[l];
-    BGP_TRY(launch_level(h, L, h->d_U.p, h->n, L.ucol + L.r, L.ucol, 1, 0, L.ucol, s));
+    BGP_TRY(launch_level(h, L, h->top.U.p, h->n, L.ucol + L.r, L.ucol, 1, 0, L.ucol, s));
   }
   const int nl = (int)h->leaves.size();
   int ndesc = 0;
@@ -884,7 +938,7 @@ static int hodlr_finish_top_impl(bgp_hodlr* h, bool allreduce) {
 // sharded compute with the library's communicator: all-gather of the locally solved rows of the top-level factor panel
 // (the ONE data-path collective of compute()), then the top nodes, then the log-det all-reduce.
 static int hodlr_exchange_finish(bgp_hodlr* h) {
-  BGP_TRY(exchange_rows(h, h->d_U.p, h->n, top_cols(h), h->sA));
+  BGP_TRY(exchange_rows(h, h->top.U.p, h->n, top_cols(h), h->sA));
   BGP_TRY(hodlr_finish_top_impl(h, true));
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->t_ms[0] = ms;
@@ -915,7 +969,7 @@ void bgp_hodlr_destroy(bgp_hodlr_t* h) {
   }
   // release buffers while the streams are still alive
   h->d_prog.release(); h->d_x.release(); h->d_yerr.release(); h->d_diag.release(); h->d_L.release();
-  h->d_leaf_logdet.release(); h->d_node_logdet.release(); h->d_V.release(); h->d_U.release(); h->d_S.release();
+  h->d_leaf_logdet.release(); h->d_node_logdet.release(); h->top.V.release(); h->top.U.release(); h->loc.V.release(); h->loc.U.release(); h->d_S.release();
   h->d_W.release(); h->d_scalar.release(); h->d_rhs.release(); h->d_leaves.release(); h->d_aca.release();
   h->d_aca_out.release(); h->d_nodes.release(); h->d_idx.release(); h->d_piv_rows.release(); h->d_piv_cols.release();
   h->lu_ws.d_nodes.release(); h->lu_ws.d_trsm.release(); h->lu_ws.d_gemm.release(); h->d_gram_desc.release(); h->d_upd_desc.release();
@@ -1156,9 +1210,10 @@ int bgp_selftest_gemm(int32_t a_kcontig, int32_t b_kcontig, int32_t m, int32_t n
 int bgp_hodlr_top_panel(bgp_hodlr_t* h, double** ptr_dev, int64_t* row0, int64_t* rows, int64_t* cols, int64_t* ld) {
   if (!h) { set_error("null handle"); return BGP_ERR_INVALID; }
   const int cut = std::min<int>(h->cut_depth, (int)h->levels.size());
-  *ptr_dev = h->d_U.p;
+  *ptr_dev = h->top.U.p;
   *row0 = h->row0; *rows = h->nloc;
-  *cols = cut < (int)h->levels.size() ? h->levels[cut].ucol : h->rtot;
+  (void)cut;
+  *cols = h->top.ucols;
   *ld = h->n;
   return BGP_OK;
 }
@@ -1175,7 +1230,7 @@ int bgp_hodlr_export_top(bgp_hodlr_t* h, double* buf_dev, int64_t rows_pad) {
   const int64_t cols = top_cols(h);
   if (cols == 0 || h->nloc == 0) return BGP_OK;
   if (rows_pad < h->nloc) { set_error("rows_pad too small"); return BGP_ERR_INVALID; }
-  pack_rows_kernel<<<1184, 256, 0, h->sA>>>(h->d_U.p, h->n, h->row0, h->nloc, cols, buf_dev, rows_pad);
+  pack_rows_kernel<<<1184, 256, 0, h->sA>>>(h->top.U.p, h->n, h->row0, h->nloc, cols, buf_dev, rows_pad);
   BGP_LAUNCH_CHECK();
   BGP_CUDA(cudaStreamSynchronize(h->sA));
   return BGP_OK;
@@ -1187,7 +1242,7 @@ int bgp_hodlr_import_top(bgp_hodlr_t* h, const double* all_buf_dev, int64_t rows
   if (cols == 0) return BGP_OK;
   for (size_t s = 0; s < h->shard_rows.size(); ++s) {
     if ((int)s == h->opts.shard_rank) continue;  // own rows are already in place
-    unpack_rows_kernel<<<1184, 256, 0, h->sA>>>(h->d_U.p, h->n, h->shard_row0[s], h->shard_rows[s], cols,
+    unpack_rows_kernel<<<1184, 256, 0, h->sA>>>(h->top.U.p, h->n, h->shard_row0[s], h->shard_rows[s], cols,
                                                 all_buf_dev + (int64_t)s * cols * rows_pad, rows_pad);
     BGP_LAUNCH_CHECK();
   }

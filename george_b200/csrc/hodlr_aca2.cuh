@@ -43,6 +43,10 @@ struct A2Node {  // static description
   int cchunk0, n_cchunks, rchunk0, n_rchunks;
   int bmax, is_top;  // is_top: node above the shard cut, its candidate scan is split across ranks by column chunk
   int64_t idx_off, piv_off, cand_off;
+  double* vbase;   // column 0 of this node's level in ITS factor panel, addressed by GLOBAL row index: the panel of a level
+                   // owned by one shard holds only that shard's rows (leading dimension ld = rows of the shard) and vbase
+                   // points row0_shard entries before its allocation; levels above the shard cut span all N rows
+  int64_t ld;
 };
 
 struct A2State {  // dynamic
@@ -140,8 +144,6 @@ struct A2Args {
   A2State* states;
   MT19937* rngs;   // [2 * node]: committed stream, [2 * node + 1]: stream after the whole pending batch
   int n_nodes;
-  double* Vp;
-  int64_t ld;
   double tol;
   uint32_t seed;
   int exhaust_mode;
@@ -357,7 +359,7 @@ __device__ inline void a2_generate(const A2Args& a, A2State& st, A2NodeSmem& S, 
     if (threadIdx.x == 0) S.n_live = B;
   } else {
     const double clo = a.node_box[2 * nid], chi = a.node_box[2 * nid + 1];
-    const double* Ucol = a.Vp + (int64_t)nd.vcol * a.ld + nd.row0;
+    const double* Ucol = nd.vbase + nd.row0;
     const double* xr = a.x + nd.row0;
     constexpr int G = 4;  // candidates per trip: their (dependent, uncoalesced) loads are issued together
     for (int c0 = threadIdx.x; c0 < B; c0 += G * blockDim.x) {
@@ -372,7 +374,7 @@ __device__ inline void a2_generate(const A2Args& a, A2State& st, A2NodeSmem& S, 
       for (int q = 0; q < rank; ++q) {
         double u[G];
 #pragma unroll
-        for (int j = 0; j < G; ++j) u[j] = __ldcg(Ucol + (int64_t)q * a.ld + row[j]);
+        for (int j = 0; j < G; ++j) u[j] = __ldcg(Ucol + (int64_t)q * nd.ld + row[j]);
 #pragma unroll
         for (int j = 0; j < G; ++j) b[j] += fabs(u[j]);
       }
@@ -477,7 +479,7 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
   const int w_lo = lc * A2_CHUNK + warp * A2_GROUP;  // first column of this warp
   const int w_n = min(A2_GROUP, nd.n_cols - w_lo);
   if (w_n <= 0) return;
-  const double* Vcols = a.Vp + (int64_t)nd.vcol * a.ld;
+  const double* Vcols = nd.vbase;
   const double* xr = a.x + (int64_t)nd.row0 * ndim;
   const double* xc = a.x + (int64_t)(nd.col0 + w_lo) * ndim;
   const int* cand = a.cand + nd.cand_off;
@@ -541,8 +543,8 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
       }
       int k = 0;
       for (; k + 2 <= rank; k += 2) {  // two factor columns per trip: the loads of the second overlap the FMAs of the first
-        const double* vc0 = Vcols + (int64_t)k * a.ld;
-        const double* vc1 = vc0 + a.ld;
+        const double* vc0 = Vcols + (int64_t)k * nd.ld;
+        const double* vc1 = vc0 + nd.ld;
         double vk0[A2_EPT], vk1[A2_EPT], u0[A2_CG], u1[A2_CG];
 #pragma unroll
         for (int c = 0; c < A2_CG; ++c) { u0[c] = __ldcg(vc0 + nd.row0 + row[c]); u1[c] = __ldcg(vc1 + nd.row0 + row[c]); }
@@ -554,7 +556,7 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
           for (int e = 0; e < A2_EPT; ++e) { vals[c][e] -= u0[c] * vk0[e]; vals[c][e] -= u1[c] * vk1[e]; }
       }
       for (; k < rank; ++k) {
-        const double* vcol = Vcols + (int64_t)k * a.ld;
+        const double* vcol = Vcols + (int64_t)k * nd.ld;
         double vk[A2_EPT], u[A2_CG];
 #pragma unroll
         for (int c = 0; c < A2_CG; ++c) u[c] = __ldcg(vcol + nd.row0 + row[c]);
@@ -770,7 +772,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_vrow_kernel(A2Args a) {
   const int ndim = a.prog->ndim;
   const int rank = st.rank;
   const int c_n = min(A2_THREADS, nd.n_cols - c_lo);
-  double* Vcols = a.Vp + (int64_t)nd.vcol * a.ld;
+  double* Vcols = nd.vbase;
   const int i = st.piv_i;
   for (int q = threadIdx.x; q < ndim; q += A2_THREADS) s_x[q] = a.x[(int64_t)(nd.row0 + i) * ndim + q];
   __syncthreads();
@@ -779,11 +781,11 @@ __global__ void __launch_bounds__(A2_THREADS) a2_vrow_kernel(A2Args a) {
   const bool act = n < c_n;
   const int nn = act ? n : 0;
   const double val = a2_resid_entry(fn, s_x, a.x + (int64_t)(nd.col0 + c_lo + nn) * ndim, rank, Vcols + nd.col0 + c_lo + nn,
-                                    a.ld, Vcols + nd.row0 + i, s_u, act);
+                                    nd.ld, Vcols + nd.row0 + i, s_u, act);
   double best = -1.0, bval = 0.0;
   int bidx = 0x7fffffff;
   if (act) {
-    Vcols[(int64_t)rank * a.ld + nd.col0 + c_lo + n] = val;
+    Vcols[(int64_t)rank * nd.ld + nd.col0 + c_lo + n] = val;
     best = fabs(val); bidx = c_lo + n; bval = val;
     if (val != val) best = __longlong_as_double(0x7ff0000000000000ll);  // a NaN wins the arg-max (it ends the reference's loop)
   }
@@ -875,7 +877,7 @@ __device__ __forceinline__ void a2_vnorm_body(const A2Args& a, int chunk, int su
   const int c_lo = lc * A2_CHUNK + sub * A2_THREADS;
   if (c_lo >= nd.n_cols) return;
   const int c_n = min(A2_THREADS, nd.n_cols - c_lo);
-  double* Vcols = a.Vp + (int64_t)nd.vcol * a.ld;
+  double* Vcols = nd.vbase;
   const double pivot = st.pivot;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double vn2 = 0.0, av = 0.0;
@@ -883,7 +885,7 @@ __device__ __forceinline__ void a2_vnorm_body(const A2Args& a, int chunk, int su
     const int n = threadIdx.x;
     double v = 0.0;
     if (n < c_n) {
-      double* pv = Vcols + (int64_t)rank * a.ld + nd.col0 + c_lo + n;
+      double* pv = Vcols + (int64_t)rank * nd.ld + nd.col0 + c_lo + n;
       v = *pv / pivot;
       *pv = v;
       vn2 = v * v;
@@ -905,7 +907,7 @@ __device__ __forceinline__ void a2_vnorm_body(const A2Args& a, int chunk, int su
   }
   double* part = a.vpart + ((int64_t)chunk * A2_NSUB + sub) * (a.capmax + 1);
   if (threadIdx.x == 0) part[0] = vn2;
-  a2_partial_dots(Vcols + nd.col0 + c_lo, a.ld, rank, s_v, c_n, part);
+  a2_partial_dots(Vcols + nd.col0 + c_lo, nd.ld, rank, s_v, c_n, part);
 }
 
 // ---- ucol: column residual -> panel column `rank` (row part), partial ||u||^2 and U_prev^T u --------------------
@@ -932,7 +934,7 @@ __global__ void __launch_bounds__(A2_THREADS) a2_vnorm_ucol_kernel(A2Args a, int
   const int ndim = a.prog->ndim;
   const int rank = st.rank;
   const int r_n = min(A2_THREADS, nd.n_rows - r_lo);
-  double* Vcols = a.Vp + (int64_t)nd.vcol * a.ld;
+  double* Vcols = nd.vbase;
   const int j = st.piv_j;
   for (int q = threadIdx.x; q < ndim; q += A2_THREADS) s_x[q] = a.x[(int64_t)(nd.col0 + j) * ndim + q];
   __syncthreads();
@@ -941,18 +943,18 @@ __global__ void __launch_bounds__(A2_THREADS) a2_vnorm_ucol_kernel(A2Args a, int
   const bool act = n < r_n;
   const int nn = act ? n : 0;
   // V(j, q) for q < rank: columns already normalised in earlier iterations
-  const double val = a2_resid_entry(fn, a.x + (int64_t)(nd.row0 + r_lo + nn) * ndim, s_x, rank, Vcols + nd.row0 + r_lo + nn, a.ld,
+  const double val = a2_resid_entry(fn, a.x + (int64_t)(nd.row0 + r_lo + nn) * ndim, s_x, rank, Vcols + nd.row0 + r_lo + nn, nd.ld,
                                     Vcols + nd.col0 + j, s_vr, act);
   double un2 = 0.0;
   if (act) {
-    Vcols[(int64_t)rank * a.ld + nd.row0 + r_lo + n] = val;
+    Vcols[(int64_t)rank * nd.ld + nd.row0 + r_lo + n] = val;
     un2 = val * val;
   }
   s_u[n] = act ? val : 0.0;
   un2 = block_sum(un2, red);
   double* part = a.upart + ((int64_t)chunk * A2_NSUB + sub) * (a.capmax + 1);
   if (threadIdx.x == 0) part[0] = un2;
-  a2_partial_dots(Vcols + nd.row0 + r_lo, a.ld, rank, s_u, r_n, part);
+  a2_partial_dots(Vcols + nd.row0 + r_lo, nd.ld, rank, s_u, r_n, part);
 }
 inline void a2_vrow_launch(int shape, dim3 grid, cudaStream_t s, const A2Args& a) {
   BGP_SHAPE_SWITCH(shape, (a2_vrow_kernel<SHAPE><<<grid, A2_THREADS, 0, s>>>(a)));
@@ -1070,7 +1072,7 @@ __global__ void __launch_bounds__(256) a2_dense_fill_kernel(A2Args a) {
   const double* xr = a.x + (int64_t)nd.row0 * ndim;
   const double* xc = a.x + (int64_t)nd.col0 * ndim;
   for (int m = blockIdx.y; m < nd.n_cols; m += gridDim.y) {
-    double* vc = a.Vp + (int64_t)(nd.vcol + m) * a.ld;
+    double* vc = nd.vbase + (int64_t)m * nd.ld;
     for (int n = threadIdx.x; n < nd.n_cols; n += blockDim.x) vc[nd.col0 + n] = (n == m) ? 1.0 : 0.0;
     for (int n = threadIdx.x; n < nd.n_rows; n += blockDim.x)
       vc[nd.row0 + n] = kernel_value(P, xr + (int64_t)n * ndim, xc + (int64_t)m * ndim);
