@@ -397,6 +397,19 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total = float(t.item())
 
+    if rank == 0:  # (kept on stderr so that a failure in the second leg does not lose the first)
+        sys.stderr.write("[bench] value leg: {0:.3f} ms/step over {1} steps, N={2}, world={3}, log-lik {4!r}\n".format(
+            1e3 * total / args.steps, args.steps, n, world, ll_value))
+        sys.stderr.flush()
+    if world > 1:
+        # the sharded handle owns tens of GB of factor panels at the largest sizes: release them (back into the stream-ordered
+        # pool, where the GP's own handle below finds blocks of the right sizes) before the second leg builds its solver
+        sharded.solver = None
+        del sharded
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+
     # ---------------- leg 2: end to end through the public GP API with pinned HOST buffers (e2e) ----------------
     hx, px = pinned_array(lib, n)
     hyerr, pyerr = pinned_array(lib, n)
