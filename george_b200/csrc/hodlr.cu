@@ -952,7 +952,8 @@ extern "C" {
 
 void bgp_hodlr_default_opts(bgp_hodlr_opts_t* o) {
   o->min_size = 100; o->seed = 42; o->tol = 0.1;  // _hodlr.cpp:202
-  o->rng_mode = BGP_RNG_PER_NODE; o->rank_capacity = 0; o->shard_rank = 0; o->shard_count = 1; o->exhaust_mode = BGP_EXHAUST_DENSE;
+  o->rng_mode = BGP_RNG_REFERENCE;  // at the default tol the answer depends on the pivots: reproduce the reference's order
+  o->rank_capacity = 0; o->shard_rank = 0; o->shard_count = 1; o->exhaust_mode = BGP_EXHAUST_DENSE;
 }
 
 int bgp_hodlr_create(bgp_hodlr_t** out) {

@@ -672,8 +672,8 @@ __global__ void __launch_bounds__(GT_THREADS) gram_tn_kernel(const NodeDesc* __r
 
 // ---------------------------------------------------------------------------------------------------------------
 // K6b: per-node small dense step (hodlr.h:228-234 factorize, :90-93 log-det, :250 lu_.solve)
-//   factor != 0: S = [[I, W_1[:, own]], [W_0[:, own], I]] (2r x 2r), LU with partial pivoting (Eigen uses complete
-//                pivoting; same determinant / solution up to rounding), log|det| -> node_logdet, LU stored.
+//   factor != 0: S = [[I, W_1[:, own]], [W_0[:, own], I]] (2r x 2r), LU with COMPLETE pivoting and the rank-revealing
+//                solve of Eigen::FullPivLU (what the reference calls), log|det| -> node_logdet, LU stored.
 //   then T = S^-1 [W_1[:, cols] ; W_0[:, cols]] for the `ncols - own` target columns, written back over W
 //   (T_top -> W_1, T_bot -> W_0 so the update kernel reads half h's coefficients from W_{1-h}... see update_nn_kernel).
 // One CTA per node, S in shared memory: the path for 2r <= SS_MAX_N; larger ranks go through hodlr_lu.cuh.
@@ -699,6 +699,11 @@ __global__ void __launch_bounds__(SS_THREADS) small_solve_kernel(const NodeDesc*
   int* piv = reinterpret_cast<int*>(Sg + (int64_t)n2 * n2);
   double* S = ss_smem;
 
+  // Eigen::FullPivLU semantics (hodlr.h:24,233,250): complete pivoting, P S Q = L U; solve() treats the pivots below
+  // eps * n * |max pivot| as zero (rank-revealing pseudo-solve); log|det| sums log|u_kk| over ALL pivots (hodlr.h:90-93).
+  int* rowt = piv;          // row transpositions
+  int* colt = piv + n2;     // column transpositions
+  int* meta = piv + 2 * n2; // [0] numerical rank used by solve()
   if (factor) {
     for (int t = threadIdx.x; t < n2 * n2; t += SS_THREADS) {
       const int i = t % n2, j = t / n2;
@@ -708,29 +713,49 @@ __global__ void __launch_bounds__(SS_THREADS) small_solve_kernel(const NodeDesc*
       S[(int64_t)j * n2 + i] = v;
     }
     __syncthreads();
-    double logdet = 0.0;
+    double logdet = 0.0, maxpivot = 0.0;
+    int nonzero = n2;
     for (int k = 0; k < n2; ++k) {
-      // pivot search in column k
+      // pivot search over the trailing block, first maximum in column-major order (Eigen's maxCoeff visitor)
       double best = -1.0;
       int bi = 0x7fffffff;
-      for (int i = k + threadIdx.x; i < n2; i += SS_THREADS) {
-        const double a = fabs(S[(int64_t)k * n2 + i]);
-        if (a > best) { best = a; bi = i; }
+      const int rem0 = n2 - k;
+      for (int t = threadIdx.x; t < rem0 * rem0; t += SS_THREADS) {
+        const int i = k + t % rem0, j = k + t / rem0;
+        const double a = fabs(S[(int64_t)j * n2 + i]);
+        const int lin = j * n2 + i;
+        if (a > best || (a == best && lin < bi)) { best = a; bi = lin; }
       }
       block_argmax(best, bi, red, redi);
-      if (threadIdx.x == 0) { s_piv = bi; piv[k] = bi; }
+      if (threadIdx.x == 0) s_piv = bi;
       __syncthreads();
-      const int p = s_piv;
-      if (p != k) {
+      const int lin = s_piv;
+      const int pr = lin % n2, pc = lin / n2;
+      const double pv = fabs(S[(int64_t)pc * n2 + pr]);
+      if (pv == 0.0) {  // the rest of the matrix is exactly zero: FullPivLU stops here (m_nonzero_pivots = k)
+        nonzero = k;
+        for (int q = k + threadIdx.x; q < n2; q += SS_THREADS) { rowt[q] = q; colt[q] = q; }
+        break;
+      }
+      maxpivot = fmax(maxpivot, pv);
+      if (threadIdx.x == 0) { rowt[k] = pr; colt[k] = pc; }
+      if (pr != k) {
         for (int jj = threadIdx.x; jj < n2; jj += SS_THREADS) {
           const double a = S[(int64_t)jj * n2 + k];
-          S[(int64_t)jj * n2 + k] = S[(int64_t)jj * n2 + p];
-          S[(int64_t)jj * n2 + p] = a;
+          S[(int64_t)jj * n2 + k] = S[(int64_t)jj * n2 + pr];
+          S[(int64_t)jj * n2 + pr] = a;
+        }
+      }
+      __syncthreads();
+      if (pc != k) {
+        for (int ii = threadIdx.x; ii < n2; ii += SS_THREADS) {
+          const double a = S[(int64_t)k * n2 + ii];
+          S[(int64_t)k * n2 + ii] = S[(int64_t)pc * n2 + ii];
+          S[(int64_t)pc * n2 + ii] = a;
         }
       }
       __syncthreads();
       const double dkk = S[(int64_t)k * n2 + k];
-      if (threadIdx.x == 0) logdet += log(fabs(dkk));
       const double inv = 1.0 / dkk;
       __syncthreads();
       for (int i = k + 1 + threadIdx.x; i < n2; i += SS_THREADS) S[(int64_t)k * n2 + i] *= inv;
@@ -742,7 +767,15 @@ __global__ void __launch_bounds__(SS_THREADS) small_solve_kernel(const NodeDesc*
       }
       __syncthreads();
     }
-    if (threadIdx.x == 0) node_logdet[node_base + blockIdx.x] = logdet;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 0; k < n2; ++k) logdet += log(fabs(S[(int64_t)k * n2 + k]));  // -inf for an exactly singular S, as the reference
+      const double thr = maxpivot * 2.220446049250313e-16 * (double)n2;           // FullPivLU::threshold() * |maxPivot|
+      int rk = 0;
+      for (int k = 0; k < nonzero; ++k) rk += (fabs(S[(int64_t)k * n2 + k]) > thr) ? 1 : 0;
+      meta[0] = rk;
+      node_logdet[node_base + blockIdx.x] = logdet;
+    }
     for (int t = threadIdx.x; t < n2 * n2; t += SS_THREADS) Sg[t] = S[t];
     __syncthreads();
   } else {
@@ -751,22 +784,27 @@ __global__ void __launch_bounds__(SS_THREADS) small_solve_kernel(const NodeDesc*
   }
 
   // solve for the target columns: one thread per column; rhs = [W1[:, c]; W0[:, c]] (hodlr.h:248-250)
+  const int rk = meta[0];
   for (int c = threadIdx.x; c < ncols; c += SS_THREADS) {
     if (factor && c >= own_off && c < own_off + r) continue;  // own columns only feed S
     double* tc = W1 + (int64_t)c * n2;  // the column's 2r entries are contiguous: [W_1(:, c); W_0(:, c)]
-    auto get = [&](int i) -> double& { return tc[i]; };
     for (int k = 0; k < n2; ++k) {
-      const int p = piv[k];
-      if (p != k) { const double a = get(k); get(k) = get(p); get(p) = a; }
+      const int p = rowt[k];
+      if (p != k) { const double a = tc[k]; tc[k] = tc[p]; tc[p] = a; }
     }
     for (int k = 0; k < n2; ++k) {
-      const double bk = get(k);
-      for (int i = k + 1; i < n2; ++i) get(i) -= S[(int64_t)k * n2 + i] * bk;
+      const double bk = tc[k];
+      for (int i = k + 1; i < n2; ++i) tc[i] -= S[(int64_t)k * n2 + i] * bk;
     }
+    for (int k = rk - 1; k >= 0; --k) {
+      const double bk = tc[k] / S[(int64_t)k * n2 + k];
+      tc[k] = bk;
+      for (int i = 0; i < k; ++i) tc[i] -= S[(int64_t)k * n2 + i] * bk;
+    }
+    for (int k = rk; k < n2; ++k) tc[k] = 0.0;
     for (int k = n2 - 1; k >= 0; --k) {
-      const double bk = get(k) / S[(int64_t)k * n2 + k];
-      get(k) = bk;
-      for (int i = 0; i < k; ++i) get(i) -= S[(int64_t)k * n2 + i] * bk;
+      const int p = colt[k];
+      if (p != k) { const double a = tc[k]; tc[k] = tc[p]; tc[p] = a; }
     }
   }
 }

@@ -18,28 +18,65 @@ from .. import _lib
 from .._spec import HodlrNodeInfo, HodlrOpts, flatten
 
 RNG_MODES = {"pernode": 0, "reference": 1}
+
+
+def resolve_rng_mode(rng_mode, tol):
+    """``None`` -> the reference's own stream order when the result depends on the pivots (``tol > 1e-6``; at the
+    reference's default ``tol = 0.1`` the HODLR answer is 3e-3 away from the dense one), the
+    level-parallel per-node streams when it does not."""
+    if rng_mode is None:
+        return "reference" if tol > 1e-6 else "pernode"
+    return rng_mode
 EXHAUST_MODES = {"dense": 0, "lowrank": 1}
 
 
 class HODLRSolver(object):
 
+    # Native handles outlive the Python objects that use them.  The reference builds a brand-new solver on every
+    # ``GP.compute`` (gp.py:327); a native handle is only device buffers, the rank capacities its last factorisation
+    # ended with and the instantiated CUDA graph of the ACA loop, all of which the next compute() of the same shape
+    # reuses — so a dying solver parks its handle here and the next one picks it up (state is overwritten by compute()).
+    _parked = []
+    _max_parked = 2
+
     def __init__(self):
         self._lib = _lib.load()
-        self._ptr = C.c_void_p()
-        _lib.check(self._lib.bgp_hodlr_create(C.byref(self._ptr)))
+        if HODLRSolver._parked:
+            self._ptr = HODLRSolver._parked.pop()
+        else:
+            self._ptr = C.c_void_p()
+            _lib.check(self._lib.bgp_hodlr_create(C.byref(self._ptr)))
         self._n = 0
+        self._fresh = True  # nothing computed through THIS object yet (a parked handle still holds its previous state)
 
     def __del__(self):
         if getattr(self, "_ptr", None) is not None and self._ptr:
-            self._lib.bgp_hodlr_destroy(self._ptr)
+            try:
+                if len(HODLRSolver._parked) < HODLRSolver._max_parked:
+                    HODLRSolver._parked.append(self._ptr)
+                else:
+                    self._lib.bgp_hodlr_destroy(self._ptr)
+            except Exception:  # interpreter shutdown
+                pass
             self._ptr = None
+
+    @classmethod
+    def release_parked(cls):
+        """Destroy the parked native handles (frees their device buffers)."""
+        lib = _lib.load()
+        while cls._parked:
+            lib.bgp_hodlr_destroy(cls._parked.pop())
 
     @property
     def computed(self):
+        if self._fresh:
+            return 0
         return int(self._lib.bgp_hodlr_computed(self._ptr))
 
     @property
     def log_determinant(self):
+        if self._fresh:
+            raise RuntimeError("the solver has not been computed")
         out = C.c_double()
         _lib.check(self._lib.bgp_hodlr_log_determinant(self._ptr, C.byref(out)))
         return out.value
@@ -54,8 +91,9 @@ class HODLRSolver(object):
         o.exhaust_mode = EXHAUST_MODES[exhaust] if isinstance(exhaust, str) else int(exhaust)
         return o
 
-    def compute(self, kernel_spec, x, yerr, min_size=100, tol=0.1, seed=42, rng_mode="pernode", rank_capacity=0,
+    def compute(self, kernel_spec, x, yerr, min_size=100, tol=0.1, seed=42, rng_mode=None, rank_capacity=0,
                 shard_rank=0, shard_count=1, exhaust="dense"):
+        rng_mode = "pernode" if shard_count > 1 and rng_mode is None else resolve_rng_mode(rng_mode, tol)
         x = np.ascontiguousarray(x, dtype=np.float64)
         if x.ndim != 2:
             raise ValueError("array has incorrect number of dimensions: {0}; expected 2".format(x.ndim))
@@ -65,11 +103,17 @@ class HODLRSolver(object):
         spec = flatten(kernel_spec)
         o = self._opts(min_size, tol, seed, rng_mode, rank_capacity, shard_rank, shard_count, exhaust)
         self._n = x.shape[0]
+        self._fresh = False
         _lib.check(self._lib.bgp_hodlr_compute(self._ptr, C.byref(spec), _lib.ptr(x), x.shape[0], x.shape[1],
                                                _lib.ptr(yerr), C.byref(o)))
         return 0
 
+    def _require_computed(self):
+        if self._fresh:
+            raise RuntimeError("the solver has not been computed")
+
     def apply_inverse(self, x, in_place=False):
+        self._require_computed()
         x = np.asarray(x)
         if in_place and x.dtype == np.float64 and x.flags.f_contiguous and x.flags.writeable and x.ndim == 2:
             b = x
@@ -85,6 +129,7 @@ class HODLRSolver(object):
         return b
 
     def dot_solve(self, x):
+        self._require_computed()
         x = np.ascontiguousarray(x, dtype=np.float64)
         if x.shape != (self._n,):
             raise ValueError("dimension mismatch")
@@ -93,6 +138,7 @@ class HODLRSolver(object):
         return out.value
 
     def get_inverse(self):
+        self._require_computed()
         # the library solves against a COLUMN-major identity; the HODLR inverse is symmetric only to `tol`, so hand the
         # buffer back with the orientation the reference's Eigen -> numpy conversion has (_hodlr.cpp:193-199): M[i, j]
         out = np.empty((self._n, self._n), dtype=np.float64)

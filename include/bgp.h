@@ -221,6 +221,10 @@ typedef struct bgp_hodlr_opts {
 } bgp_hodlr_opts_t;
 enum { BGP_EXHAUST_DENSE = 0, BGP_EXHAUST_LOWRANK = 1 };
 
+/* The reference's defaults (solvers/hodlr.py:43, _hodlr.cpp:202): min_size 100, tol 0.1, seed 42 — and, because at that
+ * tolerance the result depends on the pivot order, rng_mode = BGP_RNG_REFERENCE and exhaust_mode = BGP_EXHAUST_DENSE: a
+ * caller that changes nothing gets the reference's algorithm.  The level-parallel BGP_RNG_PER_NODE is the mode to choose
+ * for tight tolerances (the Python plug-in does so automatically for tol <= 1e-6) and the only one that shards. */
 void bgp_hodlr_default_opts(bgp_hodlr_opts_t* o);
 int bgp_hodlr_create(bgp_hodlr_t** out);
 void bgp_hodlr_destroy(bgp_hodlr_t* h);

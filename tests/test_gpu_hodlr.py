@@ -343,3 +343,90 @@ def test_graph_loop_equals_host_driven_loop(gpu, monkeypatch):
         assert res[True][2] == res[False][2] and res[True][3] == res[False][3], kname
         assert abs(res[True][0] - res[False][0]) <= 1e-13 * abs(res[False][0])
         assert abs(res[True][1] - res[False][1]) <= 1e-12 * abs(res[False][1])
+
+
+@pytest.mark.parametrize("kname", ["expsq", "m52", "sum"])
+def test_plugin_defaults_return_the_reference_answer(gpu, oracle, kname):
+    """A user who switches from george to this package and changes NOTHING (HODLRSolver defaults: min_size=100, tol=0.1,
+    seed=42) must get george's number.  At tol = 0.1 the HODLR answer is not the dense answer, so
+    this requires the reference's pivot order: the plug-in resolves rng_mode=None to the reference stream for
+    tol > 1e-6 (and to the level-parallel per-node streams for tight tolerances)."""
+    import george_b200 as george
+    from george_b200 import kernels as K
+    from george_b200._spec import flatten
+    from george_b200.solvers._hodlr import resolve_rng_mode
+    assert resolve_rng_mode(None, 0.1) == "reference" and resolve_rng_mode(None, 1e-10) == "pernode"
+    assert resolve_rng_mode("pernode", 0.1) == "pernode"
+    rng = np.random.default_rng(17)
+    n = 3000
+    x = np.sort(rng.uniform(0, 10 * n / 1000, n))
+    yerr = 0.1 * np.ones(n)
+    y = np.sin(x) + 0.1 * rng.normal(size=n)
+    kernel = {"expsq": np.var(y) * K.ExpSquaredKernel(1.0), "m52": 1.0 * K.Matern52Kernel(2.0),
+              "sum": 1.0 * K.ExpSquaredKernel(1.0) + 0.5 * K.ExpSine2Kernel(gamma=1.0, log_period=np.log(3.0))}[kname]
+    gp = george.GP(kernel, solver=george.HODLRSolver)   # all defaults
+    gp.compute(x, yerr)
+    ll = gp.log_likelihood(y)
+    sigma = np.sqrt(yerr ** 2 + george.gp.TINY)
+    o = oracle.HODLR(flatten(kernel), x, sigma)         # the restated reference at ITS defaults (shared rng, dense fallback)
+    ll_ref = -0.5 * (n * np.log(2 * np.pi) + o.log_determinant) - 0.5 * o.dot_solve(y)
+    assert abs(ll - ll_ref) <= 1e-6 * abs(ll_ref)
+    # ... and it is NOT what the per-node streams give at this tolerance (which is why the default matters)
+    gp2 = george.GP(kernel, solver=george.HODLRSolver, rng_mode="pernode")
+    gp2.compute(x, yerr)
+    assert np.isfinite(gp2.log_likelihood(y))
+
+
+def test_ill_conditioned_system_matches_oracle(gpu, oracle):
+    """Smooth kernel, small noise: cond(K) ~ 1e7, leaf pivots D down to 1e-4 and Woodbury matrices S with pivots spread over
+    several decades (at cond 1e11 the reference algorithm itself loses the log-det to 1e-3: nothing to compare there).  The reference factors leaves with Eigen's pivoted LDLT and S with FullPivLU (hodlr.h:23-24,227,233);
+    the device uses un-pivoted LDL^T (equal for SPD leaves up to rounding) and complete-pivoting LU with FullPivLU's
+    rank threshold.  log-det and solve must agree with the oracle at the level the conditioning allows."""
+    from george_b200 import kernels as K
+    from george_b200.solvers._hodlr import HODLRSolver
+    from george_b200._spec import flatten
+    rng = np.random.default_rng(2)
+    n = 1200
+    x = np.sort(rng.uniform(0, 12, n))[:, None]
+    yerr = 1e-2 * np.ones(n)
+    y = np.sin(x[:, 0])
+    kernel = 1.0 * K.ExpSquaredKernel(25.0)
+    for mode in ("reference", "pernode"):
+        s = HODLRSolver()
+        s.compute(kernel, x, yerr, min_size=100, tol=1e-12, seed=42, rng_mode=mode)
+        o = oracle.HODLR(flatten(kernel), x, yerr, min_size=100, tol=1e-12, seed=42, rng_mode=1 if mode == "reference" else 0)
+        assert np.isfinite(s.log_determinant)
+        assert abs(s.log_determinant - o.log_determinant) <= 1e-9 * abs(o.log_determinant)
+        a, ao = s.apply_inverse(y)[:, 0], o.apply_inverse(y)
+        assert np.linalg.norm(a - ao) <= 1e-6 * np.linalg.norm(ao)     # cond * eps ~ 1e-9 on each side
+        Kd = oracle.value_symmetric(flatten(kernel), x) + np.diag(yerr ** 2)
+        assert np.linalg.norm(Kd @ a - y) <= 1e-7 * np.linalg.norm(y)
+
+
+def test_rank_deficient_woodbury_matrix_is_truncated_like_fullpivlu(gpu, oracle):
+    """Two identical points, one in each half of the root, and NO noise: the leaves are regular but K is exactly singular,
+    so the root's 2r x 2r Woodbury matrix S is rank deficient.  Eigen::FullPivLU::solve (hodlr.h:250) drops the pivots
+    below eps * n * |max pivot| (a pseudo-solve) instead of dividing by rounding noise; the device LU follows the same
+    rule, so the solve stays finite and agrees with the restated reference."""
+    from george_b200 import kernels as K
+    from george_b200.solvers._hodlr import HODLRSolver
+    from george_b200._spec import flatten
+    rng = np.random.default_rng(8)
+    n = 140
+    x = np.sort(rng.uniform(0, 4, n))
+    x[100] = x[30]                       # same point in the left (0..69) and the right (70..139) leaf
+    x = x[:, None]
+    yerr = np.zeros(n)
+    y = np.sin(x[:, 0])
+    kernel = 1.0 * K.ExpKernel(0.25)     # rough kernel: the two leaves are well conditioned (cond ~ 1e5) without noise;
+    # exp(-|d|) is exactly rank 1 between sorted halves, so the root exhausts its rows and stores the block densely
+    # (hodlr.h:161-176): r = 70 and S is 140 x 140 with ONE vanishing pivot
+    s = HODLRSolver()
+    s.compute(kernel, x, yerr, min_size=70, tol=1e-12, seed=42, rng_mode="reference")
+    o = oracle.HODLR(flatten(kernel), x, yerr, min_size=70, tol=1e-12, seed=42, rng_mode=1)
+    assert s.nodes()[0]["rank"] == 70 and o.nodes()[0]["rank"] == 70
+    a, ao = s.apply_inverse(y)[:, 0], o.apply_inverse(y)
+    assert np.all(np.isfinite(a)) and np.all(np.isfinite(ao))
+    scale = np.linalg.norm(ao)
+    assert scale < 1e8                   # truncated: a division by the noise pivot would give ~1e15
+    assert np.linalg.norm(a - ao) <= 1e-4 * scale
