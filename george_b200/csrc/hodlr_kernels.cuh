@@ -730,9 +730,12 @@ __global__ void __launch_bounds__(SS_THREADS) small_solve_kernel(const NodeDesc*
       if (threadIdx.x == 0) s_piv = bi;
       __syncthreads();
       const int lin = s_piv;
-      const int pr = lin % n2, pc = lin / n2;
-      const double pv = fabs(S[(int64_t)pc * n2 + pr]);
-      if (pv == 0.0) {  // the rest of the matrix is exactly zero: FullPivLU stops here (m_nonzero_pivots = k)
+      const bool no_pivot = lin == 0x7fffffff;  // nothing comparable in the trailing block (all NaN): stop, log|det| = NaN
+      const int pr = no_pivot ? k : lin % n2, pc = no_pivot ? k : lin / n2;
+      // |pivot| = the maximum block_argmax returned to EVERY thread: do not re-read S here, the swaps below start as soon
+      // as a thread gets there (a thread that read the entry after a neighbour's swap would take a different branch)
+      const double pv = best;
+      if (pv == 0.0 || no_pivot) {  // the rest of the matrix is exactly zero: FullPivLU stops here (m_nonzero_pivots = k)
         nonzero = k;
         for (int q = k + threadIdx.x; q < n2; q += SS_THREADS) { rowt[q] = q; colt[q] = q; }
         break;

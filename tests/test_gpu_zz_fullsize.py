@@ -92,3 +92,31 @@ def test_config3_full_size_against_oracle_golden(gpu, n):
         k = min(2, nodes[i]["rank"], int(info[i, 0]))
         r, c = s.pivots(i, nodes[i]["rank"])
         assert list(r[:k]) == list(pr[off[i]:off[i] + k]) and list(c[:k]) == list(pc[off[i]:off[i] + k]), i
+
+
+def test_small_and_big_woodbury_paths_agree_on_a_deep_tree(gpu, monkeypatch):
+    """ExpSquared, N = 262144, leaves of 128: 2047 internal nodes on 11 levels, ranks 8..21, 205 factor columns.  Every level
+    goes through the one-CTA-per-node Woodbury step (complete-pivoting LU in shared memory) by default and through the
+    blocked LU + DMMA products when BGP_SMALL_RANK_LIMIT forces it; both must give the same log-determinant and solve
+    (regression: a thread re-reading the pivot entry after a neighbour had started the row swap took the "singular"
+    branch — NaN on ~3 % of the 1024 deepest nodes, only with many CTAs in flight)."""
+    from george_b200 import kernels
+    from george_b200.solvers._hodlr import HODLRSolver
+    n = 262144
+    rng = np.random.default_rng(1234)
+    x = np.sort(rng.uniform(0, 10 * n / 1000, n))
+    yerr = 0.1 * np.ones(n)
+    y = np.sin(x) + 0.1 * rng.normal(size=n)
+    res = {}
+    for big in (False, True):
+        if big:
+            monkeypatch.setenv("BGP_SMALL_RANK_LIMIT", "1")
+        else:
+            monkeypatch.delenv("BGP_SMALL_RANK_LIMIT", raising=False)
+        s = HODLRSolver()
+        s.compute(1.0 * kernels.ExpSquaredKernel(1.0), x[:, None], yerr, min_size=100, tol=1e-10, seed=42, exhaust="lowrank")
+        res[big] = (s.log_determinant, s.dot_solve(y))
+    monkeypatch.delenv("BGP_SMALL_RANK_LIMIT", raising=False)
+    assert np.isfinite(res[False][0]) and np.isfinite(res[False][1])
+    assert abs(res[False][0] - res[True][0]) <= 1e-11 * abs(res[True][0])
+    assert abs(res[False][1] - res[True][1]) <= 1e-9 * abs(res[True][1])
