@@ -29,12 +29,14 @@ constexpr int A2_NODE_THREADS = 1024;  // per-node kernels (init / decide / fini
 constexpr int A2_EPT = A2_CHUNK / A2_THREADS;  // elements per thread
 constexpr int A2_CG = 4;          // candidates evaluated together (register blocking)
 constexpr int A2_ITEM_CB = 8;      // candidate blocks (of A2_CG rows) per eval work item
-constexpr int A2_BMAX = 4096;     // max speculative candidates per iteration
+constexpr int A2_BMAX = 8192;     // max speculative candidates per iteration (bounded by the per-node CTA's shared memory)
+constexpr int A2_BGROW = 8;       // batch growth after a fully rejected batch: 4, 32, 256, 2048, 8192
 constexpr int A2_NSUB = 4;        // the residual kernels (vrow / ucol / vnorm) split a chunk into sub-chunks of A2_THREADS
 constexpr int A2_GROUP = A2_CHUNK / (A2_THREADS / 32);  // 128 columns: what one warp of a2_eval sweeps (bound granularity)
 constexpr int A2_NGROUP = A2_CHUNK / A2_GROUP;           // 8 groups per chunk
 static_assert(A2_NSUB * A2_THREADS == A2_CHUNK, "sub-chunks tile a chunk");
-constexpr int A2_HASH = 8192;     // open-addressing slots of the swap-pop overlay (>= 2 * A2_BMAX)
+constexpr int A2_HASH = 16384;    // open-addressing slots of the swap-pop multimap (>= 2 * A2_BMAX)
+static_assert(A2_BMAX <= 65536, "multimap values are 16-bit draw numbers");
 constexpr int A2_XWORDS = 64;     // room for the extra words consumed by Lemire rejections inside one batch
 
 struct A2Node {  // static description
@@ -182,10 +184,9 @@ struct A2Args {
 struct A2NodeSmem {
   MT19937 rng;
   int k[A2_BMAX];       // drawn positions
-  int ok[A2_BMAX];      // index[k_c] before this batch
   int ol[A2_BMAX];      // index[n_index-1-c] before this batch
   int hkey[A2_HASH];    // multimap position -> draws that write it (one slot per draw)
-  int hval[A2_HASH];
+  unsigned short hval[A2_HASH];
   uint32_t raw[A2_BMAX + A2_XWORDS]; // raw mt19937 words of the batch (+ the extra words of Lemire rejections); then
                                      // wl[c] = most recent earlier draw writing position last_c
   double red[32];
@@ -327,11 +328,10 @@ __device__ inline void a2_generate(const A2Args& a, A2State& st, A2NodeSmem& S, 
   __syncthreads();
   for (int c = threadIdx.x; c < B; c += blockDim.x) {
     const int pos = S.k[c];
-    S.ok[c] = index[pos];
     S.ol[c] = index[n_index - 1 - c];
     unsigned h = a2_hash(pos);
     while (atomicCAS(&S.hkey[h], -1, pos) != -1) h = (h + 1) & (A2_HASH - 1);
-    S.hval[h] = c;
+    S.hval[h] = (unsigned short)c;
   }
   __syncthreads();
   int* wl = reinterpret_cast<int*>(S.raw);
@@ -345,8 +345,7 @@ __device__ inline void a2_generate(const A2Args& a, A2State& st, A2NodeSmem& S, 
   for (int c = threadIdx.x; c < B; c += blockDim.x) {
     const int pos = S.k[c];
     const int wk = a2_prev_writer(S, pos, c);
-    const int row = (wk < 0) ? S.ok[c] : last_value(wk);
-    S.ok[c] = row;  // (only this thread reads ok[c])
+    const int row = (wk < 0) ? index[pos] : last_value(wk);  // (the list itself is untouched until a2_decide commits)
     cand[c] = row;
     cand_k[c] = pos;
     cand_L[c] = last_value(c);
@@ -366,7 +365,7 @@ __device__ inline void a2_generate(const A2Args& a, A2State& st, A2NodeSmem& S, 
       int row[G];
       double xi[G], b[G];
 #pragma unroll
-      for (int j = 0; j < G; ++j) { const int c = c0 + j * blockDim.x; row[j] = (c < B) ? S.ok[c] : S.ok[c0]; }
+      for (int j = 0; j < G; ++j) { const int c = c0 + j * blockDim.x; row[j] = cand[(c < B) ? c : c0]; }  // written above by this thread
 #pragma unroll
       for (int j = 0; j < G; ++j) xi[j] = xr[row[j]];
 #pragma unroll
@@ -708,7 +707,7 @@ __global__ void __launch_bounds__(A2_NODE_THREADS) a2_decide_kernel(A2Args a) {
   }
   if (threadIdx.x == 0) {
     st.n_index -= ncand;
-    st.B = min(4 * st.B, A2_BMAX);
+    st.B = min(A2_BGROW * st.B, A2_BMAX);
     if (st.n_index == 0) {
       st.fallback = 1;  // rows exhausted (hodlr.h:161); dense fill (if requested) happens after the loop
       st.phase = A2_DONE; st.active = 0;
@@ -975,7 +974,7 @@ __global__ void __launch_bounds__(A2_NODE_THREADS) a2_finish_kernel(A2Args a) {
     const A2Node nd = a.nodes[nid];
     __syncthreads();
     if (threadIdx.x == 0) {
-      st.B = min(4 * st.B, A2_BMAX);
+      st.B = min(A2_BGROW * st.B, A2_BMAX);
       if (st.n_index == 0) {
         st.fallback = 1;
         st.phase = A2_DONE; st.active = 0;
