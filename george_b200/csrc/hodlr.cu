@@ -372,6 +372,8 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
   a2_init_kernel<<<nn, A2_NODE_THREADS, sizeof(A2NodeSmem), s>>>(a);
   BGP_LAUNCH_CHECK();
   int active = nn, iters = 0;
+  int eval_minb = A2_EVAL_MINB_DEFAULT;
+  if (const char* e = getenv("BGP_EVAL_MINB")) eval_minb = atoi(e) == 3 ? 3 : 2;
   const int eval_grid = num_sms() * 6;  // persistent CTAs over the work list (2-3 resident per SM, a few rounds)
   // One lock-step iteration = eval -> decide -> vrow -> pivot -> vnorm|ucol -> finish -> tick.
   auto launch_iteration = [&](cudaStream_t st, cudaGraphConditionalHandle hnd, int use_hnd, int it_prof) -> int {
@@ -387,7 +389,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
       return BGP_OK;
     };
     BGP_TRY(mark(0));
-    a2_eval_launch(h->prog.shape, dim3(eval_grid), st, a);
+    a2_eval_launch(h->prog.shape, dim3(eval_grid), st, a, eval_minb);
     BGP_LAUNCH_CHECK();
     BGP_TRY(mark(1));
     a2_decide_kernel<<<nn, A2_NODE_THREADS, sizeof(A2NodeSmem), st>>>(a);
@@ -416,7 +418,7 @@ static int run_aca2(bgp_hodlr* h, const std::vector<AcaDesc>& descs, std::vector
     // calls compute() with the same shapes and buffers over and over.
     AcaGraphKey key;
     memset(&key, 0, sizeof(key));
-    key.a = a; key.nn = nn; key.ncc = ncc; key.nrc = nrc; key.shape = h->prog.shape; key.grid = eval_grid;
+    key.a = a; key.nn = nn; key.ncc = ncc; key.nrc = nrc; key.shape = h->prog.shape; key.grid = eval_grid * 4 + eval_minb;
     if (!h->aca_exec || memcmp(&key, &h->aca_key, sizeof(key)) != 0) {
       if (h->aca_exec) { cudaGraphExecDestroy(h->aca_exec); h->aca_exec = nullptr; }
       if (h->aca_graph) { cudaGraphDestroy(h->aca_graph); h->aca_graph = nullptr; }

@@ -30,6 +30,7 @@ constexpr int A2_EPT = A2_CHUNK / A2_THREADS;  // elements per thread
 constexpr int A2_CG = 4;          // candidates evaluated together (register blocking)
 constexpr int A2_ITEM_CB = 8;      // candidate blocks (of A2_CG rows) per eval work item
 constexpr int A2_BMAX = 8192;     // max speculative candidates per iteration (bounded by the per-node CTA's shared memory)
+constexpr int A2_EVAL_MINB_DEFAULT = 2;  // see a2_eval_kernel (BGP_EVAL_MINB=3 selects the other build at run time)
 constexpr int A2_BGROW = 8;       // batch growth after a fully rejected batch: 4, 32, 256, 2048, 8192
 constexpr int A2_NSUB = 4;        // the residual kernels (vrow / ucol / vnorm) split a chunk into sub-chunks of A2_THREADS
 constexpr int A2_GROUP = A2_CHUNK / (A2_THREADS / 32);  // 128 columns: what one warp of a2_eval sweeps (bound granularity)
@@ -589,8 +590,10 @@ __device__ __forceinline__ void a2_eval_body(const A2Args& a, const A2Node& nd, 
 }
 
 // one instantiation per program shape: the specialised ones carry no interpreter and need far fewer registers
-template <int SHAPE>
-__global__ void __launch_bounds__(A2_THREADS, 2) a2_eval_kernel(A2Args a) {
+// MINB = CTAs per SM the register allocation is made for: 2 -> 128 registers, no spills; 3 -> 80 registers and a few
+// spilled temporaries of the software exp / sqrt chains, but 24 instead of 16 warps per SM to hide their latency
+template <int SHAPE, int MINB>
+__global__ void __launch_bounds__(A2_THREADS, MINB) a2_eval_kernel(A2Args a) {
   __shared__ DevProgram P;
   // persistent CTAs sweep the work list published by the node kernels of the previous step: perfectly balanced over
   // the chip whatever mix of nodes is still active, and no empty CTAs
@@ -624,8 +627,12 @@ __global__ void __launch_bounds__(A2_THREADS, 2) a2_eval_kernel(A2Args a) {
   }
   if ((threadIdx.x & 31) == 0 && n_eval) { atomicAdd(a.stats + 3, n_eval); atomicAdd(a.stats + 1, n_fma); }
 }
-inline void a2_eval_launch(int shape, dim3 grid, cudaStream_t s, const A2Args& a) {
-  BGP_SHAPE_SWITCH(shape, (a2_eval_kernel<SHAPE><<<grid, A2_THREADS, 0, s>>>(a)));
+inline void a2_eval_launch(int shape, dim3 grid, cudaStream_t s, const A2Args& a, int minb) {
+  if (minb == 3 && shape != BGP_SHAPE_GENERIC) {
+    BGP_SHAPE_SWITCH(shape, (a2_eval_kernel<SHAPE, (SHAPE == BGP_SHAPE_GENERIC ? 2 : 3)><<<grid, A2_THREADS, 0, s>>>(a)));
+  } else {
+    BGP_SHAPE_SWITCH(shape, (a2_eval_kernel<SHAPE, 2><<<grid, A2_THREADS, 0, s>>>(a)));
+  }
 }
 
 // ---- decide: first usable candidate wins; commit the RNG / index list up to it ----------------------------------
