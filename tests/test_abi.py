@@ -64,3 +64,34 @@ def test_compute_without_device_fails_loudly():
     gp = george.GP(k, solver=george.HODLRSolver)
     with pytest.raises(_lib.BGPError):
         gp.compute(np.linspace(0, 1, 10), 0.1)
+
+
+def test_native_handles_are_parked_and_reused_but_look_fresh():
+    """The reference builds a new solver on every GP.compute (gp.py:327); the native handle behind it (device buffers,
+    rank capacities, the instantiated ACA graph) is parked by a dying Python solver and picked up by the next one.  A
+    recycled handle must look like a brand-new solver: not computed, and every query raises until compute() ran."""
+    import numpy as np
+    import pytest
+    from george_b200.solvers._hodlr import HODLRSolver, resolve_rng_mode
+    HODLRSolver.release_parked()
+    a = HODLRSolver()
+    pa = a._ptr.value
+    del a
+    assert len(HODLRSolver._parked) == 1
+    b = HODLRSolver()
+    assert b._ptr.value == pa and len(HODLRSolver._parked) == 0
+    assert b.computed == 0
+    with pytest.raises(RuntimeError):
+        b.log_determinant
+    with pytest.raises(RuntimeError):
+        b.dot_solve(np.zeros(3))
+    with pytest.raises(RuntimeError):
+        b.apply_inverse(np.zeros(3))
+    c, d, e = HODLRSolver(), HODLRSolver(), HODLRSolver()
+    del b, c, d, e                       # at most _max_parked handles are kept, the rest is destroyed
+    assert len(HODLRSolver._parked) == HODLRSolver._max_parked
+    HODLRSolver.release_parked()
+    assert HODLRSolver._parked == []
+    # default RNG order: the reference's own stream whenever the result depends on the pivots
+    assert resolve_rng_mode(None, 0.1) == "reference" and resolve_rng_mode(None, 1e-6) == "pernode"
+    assert resolve_rng_mode("reference", 1e-12) == "reference"
