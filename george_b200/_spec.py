@@ -70,6 +70,15 @@ _KERNELS = {
 }
 
 
+# user kernels compiled in from kernels/*.yml (tools/generate_kernels.py): parameters first, then constants, as above
+try:
+    from .user_kernels import USER_KERNEL_TABLE as _USER
+except ImportError:  # pragma: no cover
+    _USER = []
+for _name, _kt, _stat, _params, _consts, _doc in _USER:
+    _KERNELS[_kt] = (_stat, tuple(_params) + tuple(_consts), len(_params))
+
+
 class DimensionMismatch(RuntimeError):
     """What pybind11 turns ``george::dimension_mismatch`` (exceptions.h:8-12) into."""
 

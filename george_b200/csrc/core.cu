@@ -76,11 +76,14 @@ void dev_free(void* p, cudaStream_t s) {
   if (p) cudaFreeAsync(p, s);
 }
 
+static inline bool is_user(int kt) { return kt >= BGP_K_USER0 && kt < BGP_K_USER0 + BGP_N_USER_KERNELS; }
 static inline bool is_stationary(int kt) {
+  if (is_user(kt)) return user::kInfo[kt - BGP_K_USER0].stationary != 0;
   return kt == BGP_K_RATIONAL_QUADRATIC || kt == BGP_K_EXP || kt == BGP_K_MATERN52 || kt == BGP_K_EXP_SQUARED ||
          kt == BGP_K_MATERN32;
 }
 static inline int own_params(int kt) {
+  if (is_user(kt)) return user::kInfo[kt - BGP_K_USER0].n_params;
   switch (kt) {
     case BGP_K_LINEAR: case BGP_K_RATIONAL_QUADRATIC: case BGP_K_COSINE: case BGP_K_CONSTANT: case BGP_K_POLYNOMIAL: return 1;
     case BGP_K_LOCAL_GAUSSIAN: case BGP_K_EXP_SINE2: return 2;
@@ -110,7 +113,10 @@ int build_dev_program(const bgp_kernel_spec_t* s, DevProgram* P) {
       continue;
     }
     if (k.op != BGP_OP_KERNEL) { set_error("unrecognized operator"); return BGP_ERR_INVALID; }
-    if (k.kernel_type < 0 || k.kernel_type > BGP_K_DOT_PRODUCT) { set_error("unrecognized kernel type %d", k.kernel_type); return BGP_ERR_INVALID; }
+    if (k.kernel_type < 0 || (k.kernel_type > BGP_K_DOT_PRODUCT && !is_user(k.kernel_type))) {
+      set_error("unrecognized kernel type %d (%d user kernel(s) compiled in: tools/generate_kernels.py)", k.kernel_type, BGP_N_USER_KERNELS);
+      return BGP_ERR_INVALID;
+    }
     if (nl >= BGP_MAX_LEAVES) { set_error("invalid kernel: more than %d leaves", BGP_MAX_LEAVES); return BGP_ERR_INVALID; }
     if (k.ndim != s->ndim) { set_error("dimension mismatch between kernel leaves (%d vs %d)", k.ndim, s->ndim); return BGP_ERR_DIM; }
     if (k.naxes < 0 || k.naxes > BGP_MAX_DIM) { set_error("invalid kernel: naxes = %d", k.naxes); return BGP_ERR_INVALID; }
@@ -135,7 +141,7 @@ int build_dev_program(const bgp_kernel_spec_t* s, DevProgram* P) {
       case BGP_K_EXP_SINE2: L.rp[0] = 3.141592653589793238462643383279502884 * exp(-L.p[1]); break;
       case BGP_K_CONSTANT: L.rp[0] = exp(L.p[0]); break;
       case BGP_K_POLYNOMIAL: L.rp[0] = exp(L.p[0]); break;
-      default: break;
+      default: if (is_user(k.kernel_type)) user::reparams(k.kernel_type - BGP_K_USER0, L.p, L.rp); break;
     }
     if (is_stationary(k.kernel_type)) {
       if (k.metric_type < 0 || k.metric_type > 2) { set_error("unrecognized metric"); return BGP_ERR_INVALID; }
@@ -166,7 +172,7 @@ int build_dev_program(const bgp_kernel_spec_t* s, DevProgram* P) {
   for (int i = 0; i < nl && fast; ++i) {
     const DevLeaf& L = P->leaf[i];
     const int kt = L.kernel_type;
-    if (L.naxes != 1 || L.axes[0] != 0) fast = false;
+    if (L.naxes != 1 || L.axes[0] != 0 || is_user(kt)) fast = false;  // (user kernels run on the general interpreter path)
     else if (is_stationary(kt)) fast = (L.metric_type != BGP_METRIC_GENERAL) && !L.blocked;
     else fast = (kt == BGP_K_EXP_SINE2 || kt == BGP_K_COSINE || kt == BGP_K_CONSTANT);
   }

@@ -9,6 +9,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "user_kernels.cuh"  // generated from kernels/*.yml (tools/generate_kernels.py)
 
 namespace bgp {
 
@@ -157,6 +158,7 @@ __device__ __forceinline__ double radial_value(const DevLeaf& L, double r2) {
     case BGP_K_EXP: return exp(-sqrt(r2));
     case BGP_K_RATIONAL_QUADRATIC: return pow(1 + 0.5 * r2 / L.rp[0], -L.rp[0]);
   }
+  if (L.kernel_type >= BGP_K_USER0) return user::radial_value(L.kernel_type - BGP_K_USER0, r2, L.p, L.rp);
   return 0.0;
 }
 // dk/dr2: kernels.h:1912-1916 | 2108-2114 | 1343-1349 | Exp.yml | 454-461
@@ -168,6 +170,7 @@ __device__ __forceinline__ double radial_gradient(const DevLeaf& L, double r2) {
     case BGP_K_EXP: { if (r2 < 2.220446049250313e-16) return 0.0; const double r = sqrt(r2); return -0.5 * exp(-r) / r; }
     case BGP_K_RATIONAL_QUADRATIC: return -0.5 * pow(1 + 0.5 * r2 / L.rp[0], -L.rp[0] - 1);
   }
+  if (L.kernel_type >= BGP_K_USER0) return user::radial_gradient(L.kernel_type - BGP_K_USER0, r2, L.p, L.rp);
   return 0.0;
 }
 
@@ -183,6 +186,7 @@ __device__ __forceinline__ double axis_value(const DevLeaf& L, double x1, double
     case BGP_K_POLYNOMIAL: if (L.p[1] == 0.0) return 1.0; return pow(x1 * x2 + L.rp[0], L.p[1]);
     case BGP_K_DOT_PRODUCT: return x1 * x2;
   }
+  if (L.kernel_type >= BGP_K_USER0) return user::axis_value(L.kernel_type - BGP_K_USER0, x1, x2, L.p, L.rp);
   return 0.0;
 }
 __device__ inline double axis_param_gradient(const DevLeaf& L, int q, double x1, double x2) {
@@ -203,6 +207,7 @@ __device__ inline double axis_param_gradient(const DevLeaf& L, int q, double x1,
     case BGP_K_CONSTANT: return L.rp[0];
     case BGP_K_POLYNOMIAL: if (L.p[1] == 0.0) return 0.0; return L.rp[0] * pow(x1 * x2 + L.rp[0], L.p[1] - 1.0) * L.p[1];
   }
+  if (L.kernel_type >= BGP_K_USER0) return user::axis_param_gradient(L.kernel_type - BGP_K_USER0, q, x1, x2, L.p, L.rp);
   return 0.0;
 }
 
@@ -400,6 +405,9 @@ __device__ inline double kernel_value_grad(const DevProgram& P, const double* x1
             const double a = L.rp[0], t1 = 1.0 + 0.5 * r2 / a, t2 = 2.0 * a * t1;
             grad[off] = a * pow(t1, -a) * (r2 / t2 - log(t1));
           }
+          if (L.kernel_type >= BGP_K_USER0)  // own hyper-parameters of a stationary user kernel (kernels/*.yml grad.<param>)
+            for (int q = 0; q < L.n_params; ++q)
+              if (which[off + q]) grad[off + q] = user::radial_param_gradient(L.kernel_type - BGP_K_USER0, q, r2, L.p, L.rp);
           v = radial_value(L, r2);
         }
       } else {
@@ -449,6 +457,7 @@ __device__ inline double axis_x_gradient(const DevLeaf& L, int side, double x1, 
       return (side == 1 ? x2 : x1) * L.p[1] * pow(x1 * x2 + L.rp[0], L.p[1] - 1.0);
     case BGP_K_DOT_PRODUCT: return side == 1 ? x2 : x1;
   }
+  if (L.kernel_type >= BGP_K_USER0) return user::axis_x_gradient(L.kernel_type - BGP_K_USER0, side, x1, x2, L.p, L.rp);
   return 0.0;
 }
 __device__ inline void leaf_x_gradient(const DevLeaf& L, int ndim, int side, const double* x1, const double* x2,

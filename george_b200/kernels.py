@@ -331,6 +331,15 @@ def _bind(cls_name, order, args, kwargs):
     return bound
 
 
+# user kernels: rows generated from kernels/*.yml by tools/generate_kernels.py (the reference generates its whole
+# kernels.py this way, generate_kernels.py:10-42); the device functors are in csrc/user_kernels.cuh
+try:
+    from .user_kernels import USER_KERNEL_TABLE
+except ImportError:  # pragma: no cover
+    USER_KERNEL_TABLE = []
+_KERNEL_TABLE = _KERNEL_TABLE + [tuple(r) for r in USER_KERNEL_TABLE]
+__all__ += [r[0] for r in USER_KERNEL_TABLE]
+
 _module = sys.modules[__name__]
 for _row in _KERNEL_TABLE:
     _base, _cls = _make_kernel_class(*_row)

@@ -72,7 +72,10 @@ enum { BGP_OP_KERNEL = 0, BGP_OP_SUM = 1, BGP_OP_PRODUCT = 2 }; /* kernels.py:23
 enum {
   BGP_K_LINEAR = 0, BGP_K_RATIONAL_QUADRATIC = 1, BGP_K_EXP = 2, BGP_K_LOCAL_GAUSSIAN = 3,
   BGP_K_EMPTY = 4, BGP_K_COSINE = 5, BGP_K_MATERN52 = 6, BGP_K_EXP_SINE2 = 7, BGP_K_CONSTANT = 8,
-  BGP_K_EXP_SQUARED = 9, BGP_K_MATERN32 = 10, BGP_K_POLYNOMIAL = 11, BGP_K_DOT_PRODUCT = 12
+  BGP_K_EXP_SQUARED = 9, BGP_K_MATERN32 = 10, BGP_K_POLYNOMIAL = 11, BGP_K_DOT_PRODUCT = 12,
+  /* user kernels compiled in from kernels/*.yml by tools/generate_kernels.py (the reference's generate_kernels.py:10-42
+   * / docs/tutorials/new-kernel.rst): entry i of the sorted file list has id BGP_K_USER0 + i */
+  BGP_K_USER0 = 13
 };
 enum { BGP_METRIC_NONE = -1, BGP_METRIC_ISOTROPIC = 0, BGP_METRIC_AXIS_ALIGNED = 1, BGP_METRIC_GENERAL = 2 };
 

@@ -180,3 +180,35 @@ def test_grad_log_likelihood_uses_solver_grad_terms_and_falls_back():
     assert np.isclose(g[0], np.sum(y - 0.5))                # mean: dmu . alpha with alpha = r
     assert np.isclose(g[1], 0.5 * 0.1 * 2.0 * 6)            # white noise: 0.5 sum(exp(wn) diagA)
     assert np.isclose(g[2], 0.5 * 2.0)                      # kernel: 0.5 * g[mask] -> entry 1 of (1, 2)
+
+
+def test_user_kernel_codegen_is_up_to_date_and_wired():
+    """kernels/*.yml -> csrc/user_kernels.cuh + user_kernels.py (tools/generate_kernels.py, the counterpart of the
+    reference's generate_kernels.py:10-42): the checked-in files are what the YAML produces, the classes exist with the
+    reference's constructor conventions, and the flattened program is accepted by the library's host-side validation."""
+    import os
+    import subprocess
+    import sys
+    import ctypes as C
+    from george_b200 import kernels as K, _lib
+    from george_b200._spec import flatten
+    from george_b200.user_kernels import USER_KERNEL_TABLE, BGP_K_USER0
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "generate_kernels.py"), "--check"],
+                          stdout=subprocess.DEVNULL)
+    names = [r[0] for r in USER_KERNEL_TABLE]
+    assert names == ["CauchyKernel", "DampedCosineKernel"]
+    k1 = K.CauchyKernel(metric=2.0)                       # stationary: metric / ndim / axes / block like every built-in
+    assert k1.stationary and k1.kernel_type == BGP_K_USER0 and k1.get_parameter_names() == ("metric:log_M_0_0",)
+    k2 = K.DampedCosineKernel(log_period=0.3, log_decay=1.0, ndim=2, axes=1)
+    assert not k2.stationary and k2.kernel_type == BGP_K_USER0 + 1
+    assert k2.get_parameter_names() == ("log_period", "log_decay")
+    lib = _lib.load()
+    for kern, npar in ((k1, 1), (k2, 2), (1.5 * k1 + K.Matern32Kernel(1.0) * K.CauchyKernel(0.5), 4)):
+        spec = flatten(kern)
+        assert lib.bgp_spec_validate(C.byref(spec)) == 0
+        n = C.c_int()
+        assert lib.bgp_spec_num_params(C.byref(spec), C.byref(n)) == 0 and n.value == npar
+    bad = flatten(k1)
+    bad.nodes[0].kernel_type = BGP_K_USER0 + len(names)   # one past the last compiled-in kernel
+    assert lib.bgp_spec_validate(C.byref(bad)) != 0
