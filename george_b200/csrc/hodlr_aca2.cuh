@@ -30,7 +30,7 @@ constexpr int A2_EPT = A2_CHUNK / A2_THREADS;  // elements per thread
 constexpr int A2_CG = 4;          // candidates evaluated together (register blocking)
 constexpr int A2_ITEM_CB = 8;      // candidate blocks (of A2_CG rows) per eval work item
 constexpr int A2_BMAX = 8192;     // max speculative candidates per iteration (bounded by the per-node CTA's shared memory)
-constexpr int A2_EVAL_MINB_DEFAULT = 2;  // see a2_eval_kernel (BGP_EVAL_MINB=3 selects the other build at run time)
+constexpr int A2_EVAL_MINB_DEFAULT = 3;  // see a2_eval_kernel (BGP_EVAL_MINB=3 selects the other build at run time)
 constexpr int A2_BGROW = 8;       // batch growth after a fully rejected batch: 4, 32, 256, 2048, 8192
 constexpr int A2_NSUB = 4;        // the residual kernels (vrow / ucol / vnorm) split a chunk into sub-chunks of A2_THREADS
 constexpr int A2_GROUP = A2_CHUNK / (A2_THREADS / 32);  // 128 columns: what one warp of a2_eval sweeps (bound granularity)

@@ -117,6 +117,32 @@ class GP(ModelSet):
     def _call_white_noise(self, x):
         return self.white_noise.get_value(self._model_input(x)).flatten()
 
+    # Constant mean / white-noise models (the defaults) need no per-point array: at N ~ 10^5..10^6 every extra pass
+    # over an N-vector on the host costs about as much as a level of the factorisation on the device.
+    def _constant_of(self, model):
+        return float(model.value) if type(model) is ConstantModel else None
+
+    def _sigma(self, x):
+        """sqrt(yerr^2 + exp(white_noise(x)))  (reference gp.py:330)."""
+        c = self._constant_of(self.white_noise)
+        if c is None:
+            return np.sqrt(self._yerr2 + np.exp(self._call_white_noise(x)))
+        sigma = self._yerr2 + np.exp(c)
+        return np.sqrt(sigma, out=sigma)
+
+    def _residual_of(self, y):
+        """y - mean(x) as a contiguous float64 vector (reference gp.py:388-393); raises on a non-finite mean."""
+        c = self._constant_of(self.mean)
+        if c is None:
+            return np.ascontiguousarray(self._check_dimensions(y) - self._call_mean(self._x), dtype=np.float64)
+        if not np.isfinite(c):
+            raise ValueError("mean function returned NaN or Inf for parameters:\n{0}".format(
+                self.mean.get_parameter_dict(include_frozen=True)))
+        y = self._check_dimensions(y)
+        if c == 0.0:
+            return np.ascontiguousarray(y, dtype=np.float64)  # (no copy when y already is one)
+        return np.ascontiguousarray(y - c, dtype=np.float64)
+
     def _call_white_noise_gradient(self, x):
         return self.white_noise.get_gradient(self._model_input(x))
 
@@ -184,8 +210,7 @@ class GP(ModelSet):
 
         # a new solver per compute: the factorisation is a snapshot of the current parameters
         self.solver = self.solver_type(self.kernel, **(self.solver_kwargs))
-        sigma = np.sqrt(self._yerr2 + np.exp(self._call_white_noise(self._x)))
-        self.solver.compute(self._x, sigma, **kwargs)
+        self.solver.compute(self._x, self._sigma(self._x), **kwargs)
 
         self._const = -0.5 * (len(self._x) * np.log(2 * np.pi) + self.solver.log_determinant)
         self.computed = True
@@ -211,12 +236,11 @@ class GP(ModelSet):
         if not self.recompute(quiet=quiet):
             return -np.inf
         try:
-            mu = self._call_mean(self._x)
-        except ValueError:
-            if quiet:
+            r = self._residual_of(y)
+        except ValueError as exc:
+            if quiet and "mean function" in str(exc):
                 return -np.inf
             raise
-        r = np.ascontiguousarray(self._check_dimensions(y) - mu, dtype=np.float64)
         ll = self._const - 0.5 * self.solver.dot_solve(r)
         return ll if np.isfinite(ll) else -np.inf
 
