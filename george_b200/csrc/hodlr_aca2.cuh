@@ -284,6 +284,7 @@ __device__ inline void a2_generate(const A2Args& a, A2State& st, A2NodeSmem& S, 
     __syncthreads();
     const int c0 = S.flag;
     if (c0 == 0x7fffffff) break;
+    __syncthreads();  // every thread has read S.flag before thread 0 rewrites it below
     // redo draw c0: words raw[c0 + extra + 1], ... until one is accepted (they were already generated for later draws)
     if (threadIdx.x == 0) {
       const uint32_t srange = (uint32_t)(n_index - c0);
