@@ -98,3 +98,34 @@ def test_tree_geometry_rule(oracle):
                 assert len(cut) != p or any(nd["is_leaf"] for nd in nodes if nd["depth"] < p.bit_length() - 1)
             else:
                 assert rr == cut
+
+
+def test_lowrank_exhaust_and_pernode_modes_of_the_oracle(oracle):
+    """The two modes the CUDA path adds to the reference algorithm exist in the oracle too (so that every mode the device
+    runs has a CPU twin).  exhaust = lowrank must agree with the reference's dense fallback to rounding — every row was
+    verified below 1e-14 — while keeping ranks <= 3 for the exactly-rank-2 Matern-3/2; both must agree with dense LAPACK."""
+    from george_b200 import kernels
+    from george_b200._spec import flatten
+    rng = np.random.default_rng(5)
+    n = 1800
+    x = np.sort(rng.uniform(0, 10 * n / 1000, n))
+    yerr = 0.1 * np.ones(n)
+    y = np.sin(x) + 0.1 * rng.normal(size=n)
+    spec = flatten(1.0 * kernels.Matern32Kernel(1.0))
+    K = oracle.value_symmetric(spec, x[:, None]) + np.diag(yerr ** 2)
+    ld = np.linalg.slogdet(K)[1]
+    q = y @ np.linalg.solve(K, y)
+    res = {}
+    for rng_mode in (1, 0):
+        for exhaust in (0, 1):
+            h = oracle.HODLR(spec, x, yerr, min_size=100, tol=1e-10, seed=42, rng_mode=rng_mode, exhaust=exhaust)
+            nodes = [nd for nd in h.nodes() if not nd["is_leaf"]]
+            res[(rng_mode, exhaust)] = (h.log_determinant, h.dot_solve(y), max(nd["rank"] for nd in nodes),
+                                        sum(nd["dense_fallback"] for nd in nodes))
+            assert abs(h.log_determinant - ld) <= 1e-10 * abs(ld)
+            assert abs(h.dot_solve(y) - q) <= 1e-9 * abs(q)
+    for rng_mode in (1, 0):
+        dense, low = res[(rng_mode, 0)], res[(rng_mode, 1)]
+        assert dense[3] > 0 and low[3] == dense[3]       # the same nodes run out of rows in both modes ...
+        assert dense[2] >= 100 and low[2] <= 3           # ... the reference stores them densely, lowrank keeps rank <= 3
+        assert abs(dense[0] - low[0]) <= 1e-11 * abs(ld)
