@@ -477,14 +477,18 @@ def run_ours(args):
         flops = evaluated * EVAL_FLOPS[args.workload] + 2.0 * fmas
         achieved = flops / (ev_ms * 1e-3) * 1e-12
         traffic = None
-        try:
+        try:  # DRAM bytes of one launch of the kernel from the committed `ncu --set full` capture (read + written)
             import csv
             with open(os.path.join(ROOT, "profiles", "prof_a2_eval_r02_raw.csv")) as fh:
                 rows = list(csv.reader(fh))
-            hdr = rows[0]
-            traffic = (float(rows[2][hdr.index("dram__bytes_read.sum")]) + float(rows[2][hdr.index("dram__bytes_write.sum")])) * 1e6
+            hdr, units = rows[0], rows[1]
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            traffic = 0.0
+            for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = hdr.index(name)
+                traffic += float(rows[2][i]) * scale[units[i]]
         except Exception:
-            pass
+            traffic = None
         ph = {"leaves_concurrent_with_aca": statistics.mean(p["leaves_ms"] for p in phases),
               "aca": statistics.mean(p["aca_ms"] for p in phases), "upsweep": statistics.mean(p["upsweep_ms"] for p in phases),
               "solve": statistics.mean(p["solve_ms"] for p in phases)}
