@@ -160,13 +160,22 @@ static int launch_leaf_solve(bgp_hodlr* h, double* X, int64_t ldx, const int* nc
                              int max_cols, cudaStream_t s) {
   const int nl = (int)h->leaves.size();
   if (nl == 0 || max_cols == 0) return BGP_OK;
-  // only leaves handled locally are in d_leaves
-  dim3 grid(nl, (max_cols + LS_COLS - 1) / LS_COLS);
-  const size_t smem = sizeof(double) * (size_t)h->max_leaf * LS_COLS;
+  // only leaves handled locally are in d_leaves.  More than 8 columns (the up-sweep: every ancestor column of the leaf)
+  // go through the 32-column instantiation: the leaf factor is then streamed once per 32 columns instead of once per 8
+  // (BGP_LEAF_COLS=8 forces the narrow one).
+  int wide = max_cols > LS_COLS ? 1 : 0;
+  if (const char* e = getenv("BGP_LEAF_COLS")) wide = (atoi(e) > LS_COLS && max_cols > LS_COLS) ? 1 : 0;
+  const int cols = wide ? LS_COLS_WIDE : LS_COLS;
+  dim3 grid(nl, (max_cols + cols - 1) / cols);
+  const size_t smem = sizeof(double) * (size_t)h->max_leaf * cols;
   if (smem > 200 * 1024) { set_error("leaf size %d too large for the leaf solve kernel", h->max_leaf); return BGP_ERR_INVALID; }
-  // (the attribute is per device / context: set it on every call, it is cheap)
-  cudaFuncSetAttribute(leaf_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  leaf_solve_kernel<<<grid, LS_THREADS, smem, s>>>(h->d_leaves.p, h->d_L.p, X, ldx, ncols_by_depth, ncols_fixed, h->max_leaf);
+  if (wide) {
+    cudaFuncSetAttribute(leaf_solve_kernel<LS_COLS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    leaf_solve_kernel<LS_COLS_WIDE><<<grid, LS_THREADS, smem, s>>>(h->d_leaves.p, h->d_L.p, X, ldx, ncols_by_depth, ncols_fixed, h->max_leaf);
+  } else {
+    cudaFuncSetAttribute(leaf_solve_kernel<LS_COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    leaf_solve_kernel<LS_COLS><<<grid, LS_THREADS, smem, s>>>(h->d_leaves.p, h->d_L.p, X, ldx, ncols_by_depth, ncols_fixed, h->max_leaf);
+  }
   BGP_LAUNCH_CHECK();
   return BGP_OK;
 }

@@ -209,31 +209,35 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf_build_factor_kernel(const D
 // staged in shared memory and all threads cooperate on the substitutions.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int LS_THREADS = 256;
-constexpr int LS_COLS = 8;   // right-hand sides per CTA = warps per CTA (one warp per column in the diagonal-block phases)
-constexpr int LS_NB = 32;    // diagonal block
+constexpr int LS_COLS = 8;        // right-hand sides per CTA of the narrow instantiation (a solve: 1 .. 8 columns)
+constexpr int LS_COLS_WIDE = 32;  // ... of the wide one (the up-sweep: all ancestor columns of a leaf in one or two groups,
+                                  // so that the leaf factor is streamed once instead of once per 8 columns)
+constexpr int LS_NB = 32;         // diagonal block
 
 // Blocked substitution: per 32-column block of L, (a) the 32 x 32 diagonal block is staged in shared memory and each
-// warp solves it for one right-hand side with shuffles (no block barrier inside), (b) the rows below (forward) / the
-// columns of the block against the rows below (backward) are updated by the whole CTA with coalesced, independent loads.
-// m / 32 block steps with two barriers each instead of m dependent steps.
+// warp solves it for its right-hand sides (columns w, w + 8, ...) with shuffles (no block barrier inside), (b) the rows
+// below (forward) / the columns of the block against the rows below (backward) are updated by the whole CTA with
+// coalesced, independent loads.  m / 32 block steps with two barriers each instead of m dependent steps.
+template <int COLS>
 __global__ void __launch_bounds__(LS_THREADS) leaf_solve_kernel(const LeafDesc* __restrict__ leaves,
                                                                 const double* __restrict__ Lbuf,
                                                                 double* __restrict__ X, int64_t ldx,
                                                                 const int* __restrict__ ncols_by_depth, int ncols_fixed,
                                                                 int max_m) {
-  extern __shared__ double xs[];  // max_m x LS_COLS, column-major with leading dimension max_m
+  extern __shared__ double xs[];  // max_m x COLS, column-major with leading dimension max_m
   __shared__ double sL[LS_NB][LS_NB + 1];
   const LeafDesc lf = leaves[blockIdx.x];
   const int ncols = ncols_by_depth ? ncols_by_depth[lf.depth] : ncols_fixed;
-  const int c0 = blockIdx.y * LS_COLS;
+  const int c0 = blockIdx.y * COLS;
   if (c0 >= ncols) return;
-  const int nc = min(LS_COLS, ncols - c0);
+  const int nc = min(COLS, ncols - c0);
   const int m = lf.size;
   const double* A = Lbuf + lf.off;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int t = threadIdx.x; t < m * nc; t += LS_THREADS) {
+  constexpr int NW = LS_THREADS / 32;
+  for (int t = threadIdx.x; t < m * COLS; t += LS_THREADS) {  // (columns >= nc: zeros, so that they stay finite)
     const int i = t % m, c = t / m;
-    xs[c * max_m + i] = X[(int64_t)(c0 + c) * ldx + lf.start + i];
+    xs[c * max_m + i] = (c < nc) ? X[(int64_t)(c0 + c) * ldx + lf.start + i] : 0.0;
   }
   // ---- forward: L y = b (unit lower) ----
   for (int kb = 0; kb < m; kb += LS_NB) {
@@ -244,29 +248,29 @@ __global__ void __launch_bounds__(LS_THREADS) leaf_solve_kernel(const LeafDesc* 
       sL[i][k] = (i < nb && k < nb && i > k) ? A[(int64_t)(kb + k) * m + kb + i] : 0.0;
     }
     __syncthreads();
-    if (warp < nc) {
-      double y = (lane < nb) ? xs[warp * max_m + kb + lane] : 0.0;
+    for (int c = warp; c < nc; c += NW) {
+      double y = (lane < nb) ? xs[c * max_m + kb + lane] : 0.0;
       for (int k = 0; k < nb; ++k) {
         const double yk = __shfl_sync(0xffffffffu, y, k);
         if (lane > k) y -= sL[lane][k] * yk;
       }
-      if (lane < nb) xs[warp * max_m + kb + lane] = y;
+      if (lane < nb) xs[c * max_m + kb + lane] = y;
     }
     __syncthreads();
     const int r0 = kb + nb;
     for (int i = r0 + threadIdx.x; i < m; i += LS_THREADS) {
-      double acc[LS_COLS];
+      double acc[COLS];
 #pragma unroll
-      for (int c = 0; c < LS_COLS; ++c) acc[c] = 0.0;
+      for (int c = 0; c < COLS; ++c) acc[c] = 0.0;
       const double* Li = A + (int64_t)kb * m + i;
-#pragma unroll 8
+#pragma unroll 4
       for (int k = 0; k < nb; ++k) {
         const double l = Li[(int64_t)k * m];
 #pragma unroll
-        for (int c = 0; c < LS_COLS; ++c) acc[c] += l * xs[c * max_m + kb + k];  // (columns >= nc hold stale data: never stored)
+        for (int c = 0; c < COLS; ++c) acc[c] += l * xs[c * max_m + kb + k];
       }
 #pragma unroll
-      for (int c = 0; c < LS_COLS; ++c) if (c < nc) xs[c * max_m + i] -= acc[c];
+      for (int c = 0; c < COLS; ++c) if (c < nc) xs[c * max_m + i] -= acc[c];
     }
   }
   __syncthreads();
@@ -286,30 +290,30 @@ __global__ void __launch_bounds__(LS_THREADS) leaf_solve_kernel(const LeafDesc* 
       sL[i][k] = (i < nb && k < nb && i > k) ? A[(int64_t)(kb + k) * m + kb + i] : 0.0;
     }
     // y_k -= sum_{i >= r0} L[i][k] z_i for the columns k of this block: warp w takes k = w, w + 8, ...
-    for (int k = warp; k < nb; k += LS_THREADS / 32) {
-      double acc[LS_COLS];
+    for (int k = warp; k < nb; k += NW) {
+      double acc[COLS];
 #pragma unroll
-      for (int c = 0; c < LS_COLS; ++c) acc[c] = 0.0;
+      for (int c = 0; c < COLS; ++c) acc[c] = 0.0;
       const double* Lk = A + (int64_t)(kb + k) * m;
       for (int i = r0 + lane; i < m; i += 32) {
         const double l = Lk[i];
 #pragma unroll
-        for (int c = 0; c < LS_COLS; ++c) acc[c] += l * xs[c * max_m + i];
+        for (int c = 0; c < COLS; ++c) acc[c] += l * xs[c * max_m + i];
       }
 #pragma unroll
-      for (int c = 0; c < LS_COLS; ++c) {
+      for (int c = 0; c < COLS; ++c) {
         const double sres = warp_sum(acc[c]);
         if (lane == 0 && c < nc) xs[c * max_m + kb + k] -= sres;
       }
     }
     __syncthreads();
-    if (warp < nc) {
-      double y = (lane < nb) ? xs[warp * max_m + kb + lane] : 0.0;
+    for (int c = warp; c < nc; c += NW) {
+      double y = (lane < nb) ? xs[c * max_m + kb + lane] : 0.0;
       for (int k = nb - 1; k >= 0; --k) {
         const double zk = __shfl_sync(0xffffffffu, y, k);
         if (lane < k) y -= sL[k][lane] * zk;
       }
-      if (lane < nb) xs[warp * max_m + kb + lane] = y;
+      if (lane < nb) xs[c * max_m + kb + lane] = y;
     }
   }
   __syncthreads();
