@@ -160,10 +160,11 @@ static int launch_leaf_solve(bgp_hodlr* h, double* X, int64_t ldx, const int* nc
                              int max_cols, cudaStream_t s) {
   const int nl = (int)h->leaves.size();
   if (nl == 0 || max_cols == 0) return BGP_OK;
-  // only leaves handled locally are in d_leaves.  More than 8 columns (the up-sweep: every ancestor column of the leaf)
-  // go through the 32-column instantiation: the leaf factor is then streamed once per 32 columns instead of once per 8
-  // (BGP_LEAF_COLS=8 forces the narrow one).
-  int wide = max_cols > LS_COLS ? 1 : 0;
+  // only leaves handled locally are in d_leaves.  Column groups of 8 by default.  BGP_LEAF_COLS=32 selects the 32-column
+  // instantiation for calls with more than 8 columns (the up-sweep): it streams the leaf factor once per 32 columns
+  // instead of once per 8, but measured SLOWER on the headline (up-sweep 3.39 vs 3.06 ms: four times the serial work per
+  // CTA at 128 registers, and the 512 MB of leaf factors mostly hit in the 126 MB L2 anyway) — kept as an experiment.
+  int wide = 0;
   if (const char* e = getenv("BGP_LEAF_COLS")) wide = (atoi(e) > LS_COLS && max_cols > LS_COLS) ? 1 : 0;
   const int cols = wide ? LS_COLS_WIDE : LS_COLS;
   dim3 grid(nl, (max_cols + cols - 1) / cols);

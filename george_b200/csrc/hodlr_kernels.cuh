@@ -210,8 +210,7 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf_build_factor_kernel(const D
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int LS_THREADS = 256;
 constexpr int LS_COLS = 8;        // right-hand sides per CTA of the narrow instantiation (a solve: 1 .. 8 columns)
-constexpr int LS_COLS_WIDE = 32;  // ... of the wide one (the up-sweep: all ancestor columns of a leaf in one or two groups,
-                                  // so that the leaf factor is streamed once instead of once per 8 columns)
+constexpr int LS_COLS_WIDE = 32;  // ... of the wide one (BGP_LEAF_COLS=32; measured slower than four narrow groups, see hodlr.cu)
 constexpr int LS_NB = 32;         // diagonal block
 
 // Blocked substitution: per 32-column block of L, (a) the 32 x 32 diagonal block is staged in shared memory and each
